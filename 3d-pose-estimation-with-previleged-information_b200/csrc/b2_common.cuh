@@ -1,0 +1,120 @@
+// Shared helpers for the b2pose kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b2pose.h"
+
+void b2_set_error(const char* fmt, ...);
+
+#define B2_REQUIRE(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      b2_set_error(__VA_ARGS__);         \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define B2_LAUNCH_CHECK(what)                                                     \
+  do {                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess) {                                                     \
+      b2_set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e__));  \
+      return B2_E_LAUNCH;                                                         \
+    }                                                                             \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements <-> float4 (16 B for float, 8 B for bf16); pointers must be aligned.
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// 8 consecutive bf16 <-> 8 floats (16 B)
+__device__ __forceinline__ void load8(const bf16* p, float* f) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// fp32 value of (window / (count + 1e-6)) * clamp(count, 0, 1) exactly as partial_conv.py:41-44
+// evaluates it (fp32 add, fp32 divide, fp32 multiply; count is a small integer in fp32).
+__device__ __forceinline__ float pconv_ratio(float window, float count) {
+  float r = __fdiv_rn(window, __fadd_rn(count, 1e-6f));
+  float mo = fminf(fmaxf(count, 0.f), 1.f);
+  return __fmul_rn(r, mo);
+}
+
+static inline int b2_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// ---- internal entry points (defined in the .cu files, dispatched from api.cu) ----
+int conv_ffma_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, const void* w, const float* bias,
+                    void* y, float* mask_out, float* ratio_out, cudaStream_t st);
+int conv_ffma_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w, const float* mask_in,
+                    void* dx, cudaStream_t st);
+int conv_ffma_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy, const float* ratio,
+                    float* dw, cudaStream_t st);
+
+bool conv_tc_supported(const B2ConvDesc* d, int op);
+size_t conv_tc_workspace_bytes(const B2ConvDesc* d, int op);
+int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, const void* w, const float* bias,
+                  void* y, float* mask_out, float* ratio_out, double* bn_sums, void* workspace, cudaStream_t st);
+int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w, const float* mask_in,
+                  void* dx, void* workspace, cudaStream_t st);
+int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy, const float* ratio,
+                  float* dw, void* workspace, cudaStream_t st);

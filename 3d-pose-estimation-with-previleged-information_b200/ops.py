@@ -1,0 +1,407 @@
+"""torch.autograd bindings of the libb2pose kernels.
+
+Internal activations are NHWC-contiguous tensors ``[N, H, W, C]`` (fp32 or bf16), veils / masks
+are ``[N, H, W]`` fp32 in {0, 1}, filters are the reference's ``[K, C, R, S]`` parameters held in
+channels_last memory (= KRSC).  Every function here launches CUDA kernels through the C ABI; none
+has a PyTorch or CPU fallback.
+"""
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------- helpers
+def conv_out_size(h, w, r, s, stride, pad, dil):
+    return ((h + 2 * pad - dil * (r - 1) - 1) // stride + 1,
+            (w + 2 * pad - dil * (s - 1) - 1) // stride + 1)
+
+
+def make_desc(xshape, K, R, S, stride, pad, dil, dtype, flags):
+    N, H, W, Cin = xshape
+    Ho, Wo = conv_out_size(H, W, R, S, stride, pad, dil)
+    if Ho <= 0 or Wo <= 0:
+        raise ValueError("convolution output would be empty for input %dx%d" % (H, W))
+    return L.ConvDesc(N, H, W, Cin, K, R, S, stride, pad, dil, Ho, Wo, dtype, flags)
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per (device, stream)."""
+    if nbytes == 0:
+        return None, 0
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws, ws.numel()
+
+
+def filter_krsc(weight, dtype, shadow=None):
+    """The [K,C,R,S] parameter as a KRSC-contiguous tensor of ``dtype`` (no copy when the parameter
+    already lives in channels_last memory and has the compute dtype)."""
+    wk = weight.detach().permute(0, 2, 3, 1)
+    if dtype == weight.dtype:
+        return wk if wk.is_contiguous() else wk.contiguous()
+    if shadow is not None:
+        return shadow
+    if weight.dtype != torch.float32 or dtype != torch.bfloat16:
+        raise TypeError("unsupported filter cast %s -> %s" % (weight.dtype, dtype))
+    wk = wk if wk.is_contiguous() else wk.contiguous()
+    out = torch.empty(wk.shape, dtype=torch.bfloat16, device=wk.device)
+    L.call("b2_cast_f32_to_bf16", L.ptr(wk), L.ptr(out), wk.numel(), L.stream())
+    return out
+
+
+def to_nhwc(x, dtype):
+    """NCHW fp32/bf16 network input -> NHWC tensor of the compute dtype (no autograd)."""
+    L.require_cuda(x)
+    N, Cc, H, W = x.shape
+    x = x.detach()
+    if Cc == 1 or x.permute(0, 2, 3, 1).is_contiguous():
+        y = x.permute(0, 2, 3, 1)
+        y = y if y.is_contiguous() else y.contiguous()
+        if y.dtype == dtype:
+            return y
+        if y.dtype == torch.float32 and dtype == torch.bfloat16:
+            out = torch.empty(y.shape, dtype=dtype, device=y.device)
+            L.call("b2_cast_f32_to_bf16", L.ptr(y), L.ptr(out), y.numel(), L.stream())
+            return out
+        return y.to(dtype)
+    x = x.float().contiguous()
+    out = torch.empty((N, H, W, Cc), dtype=dtype, device=x.device)
+    L.call("b2_nchw_to_nhwc", L.ptr(x), L.ptr(out), N, Cc, H, W, L.dt(out), L.stream())
+    return out
+
+
+def veil_from_depth(depth_nhwc):
+    """veil = (depth != 0).float()  -- partial_depthnet.py:215."""
+    N, H, W, _ = depth_nhwc.shape
+    veil = torch.empty((N, H, W), dtype=torch.float32, device=depth_nhwc.device)
+    L.call("b2_veil_from_depth", L.ptr(depth_nhwc), L.ptr(veil), veil.numel(), L.dt(depth_nhwc), L.stream())
+    return veil
+
+
+def _conv_fprop(desc, x, mask, wk, bias, want_ratio, want_stats):
+    dev = x.device
+    y = torch.empty((desc.N, desc.Ho, desc.Wo, desc.K), dtype=x.dtype, device=dev)
+    partial = bool(desc.flags & L.CONV_PARTIAL)
+    mask_out = torch.empty((desc.N, desc.Ho, desc.Wo), dtype=torch.float32, device=dev) if partial else None
+    ratio = torch.empty_like(mask_out) if (partial and want_ratio) else None
+    sums = torch.zeros(2 * desc.K, dtype=torch.float64, device=dev) if want_stats else None
+    ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 0), dev)
+    L.call("b2_pconv_fprop", C.byref(desc), L.ptr(x), L.ptr(mask), L.ptr(wk), L.ptr(bias), L.ptr(y),
+           L.ptr(mask_out), L.ptr(ratio), L.ptr(sums), L.ptr(ws), wsn, L.stream())
+    return y, mask_out, ratio, sums
+
+
+def _conv_dgrad(desc, dy, ratio, wk, mask):
+    dev = dy.device
+    dx = torch.empty((desc.N, desc.H, desc.W, desc.C), dtype=dy.dtype, device=dev)
+    ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 1), dev)
+    L.call("b2_pconv_dgrad", C.byref(desc), L.ptr(dy), L.ptr(ratio), L.ptr(wk), L.ptr(mask), L.ptr(dx),
+           L.ptr(ws), wsn, L.stream())
+    return dx
+
+
+def _conv_wgrad(desc, x, mask, dy, ratio):
+    dev = dy.device
+    dw = torch.zeros((desc.K, desc.R, desc.S, desc.C), dtype=torch.float32, device=dev)
+    ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 2), dev)
+    L.call("b2_pconv_wgrad", C.byref(desc), L.ptr(x), L.ptr(mask), L.ptr(dy), L.ptr(ratio), L.ptr(dw),
+           L.ptr(ws), wsn, L.stream())
+    return dw.permute(0, 3, 1, 2)      # logical [K,C,R,S], channels_last memory
+
+
+# --------------------------------------------------------------------------- convolution
+class ConvFn(Function):
+    """(Partial) convolution.  forward(x, mask, weight, bias, shadow, cfg) -> (y, mask_out).
+
+    cfg = (stride, pad, dil, partial, premasked, force_ffma).  Backward follows the autograd of
+    partial_conv.py:46-53: dRaw = dOut*ratio, dW = wgrad(x*m, dRaw), dX = dgrad(W, dRaw)*m,
+    db = sum(dOut * mask_out).
+    """
+
+    @staticmethod
+    def forward(ctx, x, mask, weight, bias, shadow, cfg):
+        stride, pad, dil, partial, premasked, force_ffma = cfg
+        L.require_cuda(x, mask, weight, bias)
+        x = x.contiguous()
+        K, _, R, S = weight.shape
+        flags = (L.CONV_PARTIAL if partial else 0) | (L.CONV_X_PREMASKED if premasked else 0) | \
+                (L.CONV_FORCE_FFMA if force_ffma else 0)
+        desc = make_desc(x.shape, K, R, S, stride, pad, dil, L.dt(x), flags)
+        wk = filter_krsc(weight, x.dtype, shadow)
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        if partial:
+            mask = mask.contiguous()
+        y, mask_out, ratio, _ = _conv_fprop(desc, x, mask if partial else None, wk, b32, True, False)
+        ctx.desc, ctx.has_bias, ctx.wdtype = desc, bias is not None, weight.dtype
+        ctx.save_for_backward(x, mask if partial else None, wk, ratio, mask_out)
+        if partial:
+            ctx.mark_non_differentiable(mask_out)
+        return y, mask_out
+
+    @staticmethod
+    def backward(ctx, dy, _dmask):
+        x, mask, wk, ratio, mask_out = ctx.saved_tensors
+        desc = ctx.desc
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _conv_dgrad(desc, dy, ratio, wk, mask)
+        if ctx.needs_input_grad[2]:
+            dw = _conv_wgrad(desc, x, mask, dy, ratio).to(ctx.wdtype)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = torch.zeros(desc.K, dtype=torch.float32, device=dy.device)
+            rows = desc.N * desc.Ho * desc.Wo
+            L.call("b2_col_sum", L.ptr(dy), L.ptr(mask_out), L.ptr(db), rows, desc.K, L.dt(dy), L.stream())
+        return dx, None, dw, db, None, None
+
+
+class ConvBNFn(Function):
+    """conv -> BatchNorm (+ residual) (+ ReLU) (* veil) as one autograd node.
+
+    forward(x, mask, weight, shadow, gamma, beta, running_mean, running_var, residual, cfg)
+      -> (z, mask_out)
+    cfg = (stride, pad, dil, partial, premasked, relu, mask_output, training, momentum, eps, force_ffma)
+
+    The conv epilogue (or a stats kernel) produces per-channel sum / sum-of-squares, one apply
+    kernel normalises; backward is reduce + apply (which also folds the PartialConv ratio into
+    dRaw) + dgrad + wgrad.  Mirrors conv->bn->relu of partial_depthnet.py:143-157.
+    """
+
+    @staticmethod
+    def forward(ctx, x, mask, weight, shadow, gamma, beta, running_mean, running_var, residual, cfg):
+        stride, pad, dil, partial, premasked, relu, mask_output, training, momentum, eps, force_ffma = cfg
+        L.require_cuda(x, mask, weight, gamma)
+        x = x.contiguous()
+        K, _, R, S = weight.shape
+        flags = (L.CONV_PARTIAL if partial else 0) | (L.CONV_X_PREMASKED if premasked else 0) | \
+                (L.CONV_FORCE_FFMA if force_ffma else 0)
+        desc = make_desc(x.shape, K, R, S, stride, pad, dil, L.dt(x), flags)
+        wk = filter_krsc(weight, x.dtype, shadow)
+        if partial:
+            mask = mask.contiguous()
+        y, mask_out, ratio, sums = _conv_fprop(desc, x, mask if partial else None, wk, None, True, training)
+        rows = desc.N * desc.Ho * desc.Wo
+        z = torch.empty_like(y)
+        mean = torch.empty(K, dtype=torch.float32, device=x.device)
+        invstd = torch.empty_like(mean)
+        if residual is not None:
+            residual = residual.contiguous()
+        row_mask = mask_out if (mask_output and partial) else None
+        L.call("b2_bn_apply", L.ptr(y), L.ptr(sums), L.ptr(gamma), L.ptr(beta), L.ptr(running_mean),
+               L.ptr(running_var), float(momentum), float(eps), int(training), L.ptr(residual), L.ptr(row_mask),
+               int(relu), L.ptr(z), L.ptr(mean), L.ptr(invstd), rows, K, L.dt(y), L.stream())
+        ctx.desc, ctx.relu, ctx.training, ctx.wdtype = desc, relu, training, weight.dtype
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, mask if partial else None, wk, ratio, y, z, mean, invstd, gamma.detach(),
+                              row_mask if not relu else None)
+        if partial:
+            ctx.mark_non_differentiable(mask_out)
+        return z, mask_out
+
+    @staticmethod
+    def backward(ctx, dz, _dmask):
+        x, mask, wk, ratio, y, z, mean, invstd, gamma, row_mask = ctx.saved_tensors
+        desc = ctx.desc
+        dz = dz.contiguous()
+        dev = dz.device
+        K, rows = desc.K, desc.N * desc.Ho * desc.Wo
+        sums = torch.zeros(2 * K, dtype=torch.float64, device=dev)
+        L.call("b2_bn_bwd_reduce", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(row_mask),
+               int(ctx.relu), L.ptr(sums), rows, K, L.dt(dz), L.stream())
+        dy = torch.empty_like(y)
+        dres = torch.empty_like(y) if (ctx.has_res and ctx.needs_input_grad[8]) else None
+        dgamma = torch.zeros(K, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(K, dtype=torch.float32, device=dev)
+        L.call("b2_bn_bwd_apply", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+               L.ptr(sums), L.ptr(row_mask), L.ptr(ratio), int(ctx.relu), int(ctx.training), L.ptr(dy),
+               L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), rows, K, L.dt(dz), L.stream())
+        # dy now holds dRaw = dOut * ratio -> tell the conv kernels not to scale again
+        desc.flags |= L.CONV_DY_PRESCALED
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _conv_dgrad(desc, dy, None, wk, mask)
+        if ctx.needs_input_grad[2]:
+            dw = _conv_wgrad(desc, x, mask, dy, None).to(ctx.wdtype)
+        desc.flags &= ~L.CONV_DY_PRESCALED
+        return dx, None, dw, None, dgamma, dbeta, None, None, dres, None
+
+
+class MaxPoolFn(Function):
+    """MaxPool2d(3, 2, 1) on x and (optionally) the veil in one launch."""
+
+    @staticmethod
+    def forward(ctx, x, veil):
+        L.require_cuda(x, veil)
+        x = x.contiguous()
+        N, H, W, Cc = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, Ho, Wo, Cc), dtype=x.dtype, device=x.device)
+        arg = torch.empty((N, Ho, Wo, Cc), dtype=torch.uint8, device=x.device)
+        vout = None
+        if veil is not None:
+            veil = veil.contiguous()
+            vout = torch.empty((N, Ho, Wo), dtype=torch.float32, device=x.device)
+        L.call("b2_maxpool3x3s2_fwd", L.ptr(x), L.ptr(veil), L.ptr(y), L.ptr(arg), L.ptr(vout), N, H, W, Cc,
+               L.dt(x), L.stream())
+        ctx.shape = (N, H, W, Cc)
+        ctx.save_for_backward(arg)
+        if vout is not None:
+            ctx.mark_non_differentiable(vout)
+        return y, vout
+
+    @staticmethod
+    def backward(ctx, dy, _dv):
+        (arg,) = ctx.saved_tensors
+        N, H, W, Cc = ctx.shape
+        dy = dy.contiguous()
+        dx = torch.empty((N, H, W, Cc), dtype=dy.dtype, device=dy.device)
+        L.call("b2_maxpool3x3s2_bwd", L.ptr(dy), L.ptr(arg), L.ptr(dx), N, H, W, Cc, L.dt(dy), L.stream())
+        return dx, None
+
+
+# --------------------------------------------------------------------------- head
+def _logit_layout(feat):
+    """(tensor, layout): 0 = NHWC memory, 1 = NCHW memory, for a logical [N, D*J, H, W] tensor."""
+    if feat.dim() != 4:
+        raise ValueError("expected a [N, D*J, H, W] tensor")
+    if feat.permute(0, 2, 3, 1).is_contiguous() and not (feat.is_contiguous() and feat.shape[1] != 1):
+        return feat, 0
+    if feat.is_contiguous():
+        return feat, 1
+    return feat.contiguous(), 1
+
+
+class HeadFn(Function):
+    """Fused to_heatmap + decode: logits [N, D*J, H, W] -> coords [N, J, 3] (x, y, z) * depth_range."""
+
+    @staticmethod
+    def forward(ctx, feat, depth, num_joints, depth_range):
+        L.require_cuda(feat)
+        feat, layout = _logit_layout(feat)
+        N, CH, H, W = feat.shape
+        if CH != depth * num_joints:
+            raise ValueError("feature has %d channels, expected depth*num_joints = %d" % (CH, depth * num_joints))
+        dev = feat.device
+        coords = torch.empty((N, num_joints, 3), dtype=torch.float32, device=dev)
+        vmax = torch.empty((N, num_joints), dtype=torch.float32, device=dev)
+        vsum = torch.empty_like(vmax)
+        L.call("b2_head_fwd", L.ptr(feat), N, num_joints, depth, H, W, layout, L.dt(feat), float(depth_range),
+               L.ptr(coords), L.ptr(vmax), L.ptr(vsum), L.stream())
+        ctx.cfg = (N, num_joints, depth, H, W, layout, float(depth_range))
+        ctx.save_for_backward(feat, coords, vmax, vsum)
+        return coords
+
+    @staticmethod
+    def backward(ctx, dcoords):
+        feat, coords, vmax, vsum = ctx.saved_tensors
+        N, J, D, H, W, layout, rng = ctx.cfg
+        dcoords = dcoords.float().contiguous()
+        dfeat = torch.empty_like(feat)
+        L.call("b2_head_bwd", L.ptr(feat), L.ptr(dcoords), L.ptr(coords), L.ptr(vmax), L.ptr(vsum), N, J, D, H, W,
+               layout, L.dt(feat), rng, L.ptr(dfeat), L.stream())
+        return dfeat, None, None, None
+
+
+class ToHeatmapFn(Function):
+    """utils.to_heatmap (utils.py:154-175): [N, D*J, H, W] -> softmax heat-map [N, J, H, W, D] fp32."""
+
+    @staticmethod
+    def forward(ctx, feat, depth, num_joints, height, width):
+        L.require_cuda(feat)
+        feat = feat.reshape(-1, depth * num_joints, height, width)
+        feat, layout = _logit_layout(feat)
+        N = feat.shape[0]
+        dev = feat.device
+        heat = torch.empty((N, num_joints, height, width, depth), dtype=torch.float32, device=dev)
+        scratch = torch.empty((N, num_joints, 3), dtype=torch.float32, device=dev)
+        L.call("b2_heatmap_softmax", L.ptr(feat), N, num_joints, depth, height, width, layout, L.dt(feat),
+               L.ptr(heat), L.ptr(scratch), L.stream())
+        ctx.cfg = (N, num_joints, depth, height, width, layout, feat.dtype)
+        ctx.feat_like = feat
+        ctx.save_for_backward(heat)
+        return heat
+
+    @staticmethod
+    def backward(ctx, dheat):
+        (heat,) = ctx.saved_tensors
+        N, J, D, H, W, layout, dtype = ctx.cfg
+        dheat = dheat.float().contiguous()
+        dfeat = torch.empty_like(ctx.feat_like)
+        L.call("b2_heatmap_softmax_bwd", L.ptr(heat), L.ptr(dheat), N, J, D, H, W, layout, L.dt(dfeat),
+               L.ptr(dfeat), L.stream())
+        return dfeat, None, None, None, None
+
+
+class DecodeFn(Function):
+    """utils.decode (utils.py:178-194): heat-map [N, J, H, W, D] -> [N, J, 3] * depth_range."""
+
+    @staticmethod
+    def forward(ctx, heat, depth_range):
+        L.require_cuda(heat)
+        heat = heat.float().contiguous()
+        N, J, H, W, D = heat.shape
+        coords = torch.empty((N, J, 3), dtype=torch.float32, device=heat.device)
+        L.call("b2_heatmap_decode", L.ptr(heat), N, J, D, H, W, float(depth_range), L.ptr(coords), L.stream())
+        ctx.cfg = (N, J, D, H, W, float(depth_range))
+        return coords
+
+    @staticmethod
+    def backward(ctx, dcoords):
+        N, J, D, H, W, rng = ctx.cfg
+        dcoords = dcoords.float().contiguous()
+        dheat = torch.empty((N, J, H, W, D), dtype=torch.float32, device=dcoords.device)
+        L.call("b2_heatmap_decode_bwd", L.ptr(dcoords), N, J, D, H, W, rng, L.ptr(dheat), L.stream())
+        return dheat, None
+
+
+CRITERIA = {"SmoothL1": 0, "L1": 1, "MSE": 2}
+
+
+class PoseLossFn(Function):
+    """Root-relative shift + masked mean loss (depth_train.py:397-405) -> (loss, spec_cam)."""
+
+    @staticmethod
+    def forward(ctx, coords, true_cam, valid, key_index, loss_div, criterion):
+        L.require_cuda(coords, true_cam, valid)
+        coords = coords.float().contiguous()
+        true_cam = true_cam.float().contiguous()
+        valid = valid.to(torch.uint8).contiguous()
+        N, J, _ = coords.shape
+        dev = coords.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        spec = torch.empty_like(coords)
+        dcoords = torch.empty_like(coords)
+        L.call("b2_pose_loss", L.ptr(coords), L.ptr(true_cam), L.ptr(valid), N, J, int(key_index), float(loss_div),
+               CRITERIA[criterion], L.ptr(loss), L.ptr(spec), L.ptr(dcoords), L.stream())
+        ctx.save_for_backward(dcoords)
+        ctx.mark_non_differentiable(spec)
+        return loss, spec
+
+    @staticmethod
+    def backward(ctx, dloss, _dspec):
+        (dcoords,) = ctx.saved_tensors
+        return dcoords * dloss, None, None, None, None, None
+
+
+def unproject_depth(img, intrinsic):
+    """utils.to_depth on device: img [..., H, W] fp32 CUDA tensor, intrinsic 3x3 (host array-like)."""
+    import numpy as np
+    L.require_cuda(img)
+    img = img.float().contiguous()
+    H, W = img.shape[-2:]
+    K = np.asarray(intrinsic, np.float32)
+    kinv = np.linalg.inv(K[:2, :2]).astype(np.float32).reshape(-1)
+    kin = (C.c_float * 4)(*[float(v) for v in kinv])
+    cc = (C.c_float * 2)(float(K[0, 2]), float(K[1, 2]))
+    out = torch.empty_like(img)
+    L.call("b2_unproject_depth", L.ptr(img), L.ptr(out), img.numel() // (H * W), H, W, kin, cc, L.stream())
+    return out

@@ -1,0 +1,342 @@
+"""Training-step loop of the depth stream: drop-in for ``depth_train.Trainer`` (``vanilla_train``
+depth_train.py:376-462, ``fusion_train`` :286-373, ``adapt_learn_rate`` :621-638, ``*_infer``
+:650-679) and ``train.Trainer.cam_train`` (train.py:145-192).
+
+B200-first differences from the reference loop (results identical within tolerance):
+  * all parameters live in ONE flat fp32 buffer (gradients, Adam moments and the bf16 shadow
+    filters likewise), so clip-norm + Adam is two kernels instead of ~480 tensor ops and the
+    data-parallel exchange is a handful of bucketed NCCL all-reduces over contiguous memory;
+  * ``half_acc`` selects bf16 tensor-core compute with fp32 masters (no loss scaling needed); the
+    reference's inf-skip survives as a finite check inside the fused Adam kernel, without the
+    per-parameter host syncs of depth_train.py:435;
+  * the whole step (zero-grad, forward, head, loss, backward, clip, Adam) is captured in a CUDA
+    graph and replayed; the learning rate and Adam bias corrections are read from a small device
+    buffer so the schedule moves without re-capture;
+  * one process per GPU; gradients are averaged over ranks (DataParallel's gather-then-mean loss is
+    the same thing), BN statistics stay per rank like DataParallel's per-replica BN.
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops, utils
+from .layers import BatchNorm2d, _B2ConvBase
+
+_ALIGN = 64      # elements; keeps every parameter slice 256-byte (fp32) / 128-byte (bf16) aligned
+
+
+def train_args(**kw):
+    """Namespace with the reference's option names and defaults (opts.py:1-78)."""
+    base = dict(model="resnet50", half_acc=False, depth_only=True, do_fusion=False, do_teach=False,
+                partial_conv=False, pretrain=False, early_dist=False, skip_relu=False, extra_channel=False,
+                joint_space=False, warmup=1, n_epochs=20, batch_size=64, side_in=257, stride=16, num_joints=19,
+                depth=16, warmup_factor=0.2, learn_rate=5e-5, learn_decay=0.2, grad_norm=5.0, grad_scaling=32.0,
+                weight_decay=4e-5, depth_range=1000.0, loss_div=10.0, criterion="SmoothL1")
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+def synthetic_batch(n, side, num_joints, device, seed=1, invalid_frac=0.25, key_index=None, pin=False):
+    """Synthetic (color, depth, true_cam, true_val) of the dataset tuple layout
+    (depth_datasets.py:199-237): color ~ N(0,1), depth = U(0.05,1) with rectangular holes of
+    invalid (zero) pixels, joints ~ N(0, 300 mm), ~90 % valid with the root always valid."""
+    g = torch.Generator().manual_seed(seed)
+    color = torch.randn(n, 3, side, side, generator=g)
+    depth = torch.rand(n, 1, side, side, generator=g) * 0.95 + 0.05
+    lo, hi = max(2, side // 16), max(3, (side * 3) // 8)
+    for i in range(n):
+        holes = torch.ones(side, side)
+        guard = 0
+        while float(1 - holes.mean()) < invalid_frac and guard < 1000:
+            h, w = (int(v) for v in torch.randint(lo, hi + 1, (2,), generator=g))
+            top = int(torch.randint(0, max(1, side - h + 1), (1,), generator=g))
+            left = int(torch.randint(0, max(1, side - w + 1), (1,), generator=g))
+            holes[top:top + h, left:left + w] = 0
+            guard += 1
+        depth[i, 0] *= holes
+    true_cam = torch.randn(n, num_joints, 3, generator=g) * 300.0
+    true_val = torch.rand(n, num_joints, generator=g) < 0.9
+    true_val[:, (num_joints - 1) if key_index is None else key_index] = True
+    out = (color, depth, true_cam, true_val)
+    if pin:
+        return tuple(t.pin_memory() for t in out)
+    return tuple(t.to(device) for t in out) if device is not None else out
+
+
+class _FlatState:
+    """All trainable parameters (and grads / Adam moments / bf16 shadows) as views of flat buffers."""
+
+    def __init__(self, model, want_shadow):
+        params = [p for p in model.parameters() if p.requires_grad]
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.n = total
+        self.w = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.g = torch.zeros_like(self.w)
+        self.m = torch.zeros_like(self.w)
+        self.v = torch.zeros_like(self.w)
+        self.w16 = torch.zeros(total, dtype=torch.bfloat16, device=dev) if want_shadow else None
+        self.params, self.offsets = params, offs
+        owner = {}
+        for mod in model.modules():
+            if isinstance(mod, _B2ConvBase):
+                owner[id(mod.weight)] = mod
+        for p, o in zip(params, offs):
+            n = p.numel()
+            if p.dim() == 4:                       # filters: keep KRSC memory order
+                K, Cc, R, S = p.shape
+                src = p.data.permute(0, 2, 3, 1).contiguous().view(-1).float()
+                self.w[o:o + n].copy_(src)
+                p.data = self.w[o:o + n].view(K, R, S, Cc).permute(0, 3, 1, 2)
+                p.grad = self.g[o:o + n].view(K, R, S, Cc).permute(0, 3, 1, 2)
+                if want_shadow and id(p) in owner:
+                    owner[id(p)]._shadow = self.w16[o:o + n].view(K, R, S, Cc)
+            else:
+                self.w[o:o + n].copy_(p.data.view(-1).float())
+                p.data = self.w[o:o + n].view(p.shape)
+                p.grad = self.g[o:o + n].view(p.shape)
+        if want_shadow:
+            self.refresh_shadow()
+
+    def refresh_shadow(self):
+        if self.w16 is not None:
+            L.call("b2_cast_f32_to_bf16", L.ptr(self.w), L.ptr(self.w16), self.n, L.stream())
+
+
+class Trainer:
+    def __init__(self, args, model, data_info, use_graph=True, process_group=None, bucket_mb=25.0):
+        self.model = model
+        self.data_info = data_info
+        self.key_index = data_info["key_index"] if isinstance(data_info, dict) else data_info.key_index
+        g = lambda name, default: getattr(args, name, default)
+        self.half_acc = bool(g("half_acc", False))
+        self.depth_only = bool(g("depth_only", True))
+        self.do_fusion = bool(g("do_fusion", False))
+        if g("do_teach", False) or g("semi_teach", False):
+            raise NotImplementedError("distillation / semi-supervised steps are outside this hot path")
+        self.depth, self.num_joints = args.depth, args.num_joints
+        self.side_in, self.stride = args.side_in, args.stride
+        self.depth_range = g("depth_range", 1000.0)
+        self.warmup, self.learn_rate = g("warmup", 1), g("learn_rate", 5e-5)
+        self.learn_decay, self.num_epochs = g("learn_decay", 0.2), g("n_epochs", 20)
+        self.warmup_factor = g("warmup_factor", 0.2)
+        self.grad_norm, self.loss_div = g("grad_norm", 5.0), g("loss_div", 10.0)
+        self.weight_decay = g("weight_decay", 4e-5)
+        self.criterion = g("criterion", "SmoothL1")
+        if self.criterion not in ops.CRITERIA:
+            raise ValueError("criterion must be one of %s" % sorted(ops.CRITERIA))
+        self.legacy = getattr(model, "kind", "") == "resnet"           # train.py:174 has no loss_div
+        if self.half_acc:
+            self.model = self.model.half()      # bf16 compute, fp32 masters stay in the flat buffer
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("Trainer needs the model on a CUDA device; there is no CPU fallback")
+        self.device = dev
+        self.list_names = [n for n, _ in model.named_parameters()]
+        self.flat = _FlatState(model, want_shadow=self.half_acc)
+        self.list_params = self.flat.params
+        self.bns = [m for m in model.modules() if isinstance(m, BatchNorm2d)]
+        for m in self.bns:
+            m.defer_count = True
+        self.lr = self.learn_rate
+        self.step_count = 0
+        self.betas, self.eps = (0.9, 0.999), 1e-8
+        self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.use_graph = use_graph
+        self.launches_per_step = 0
+        self._graphs = {}
+        self._static = {}
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            import torch.distributed as dist
+            self.pg = process_group if process_group is not None else dist.group.WORLD
+            self.world = dist.get_world_size(self.pg)
+            from .parallel import broadcast_flat, GradBuckets
+            broadcast_flat(self.flat, self.pg)
+            self.buckets = GradBuckets(self.flat, self.pg, bucket_mb)
+            for m in model.buffers():
+                dist.broadcast(m, 0, group=self.pg)
+
+    # ------------------------------------------------------------------ schedule
+    def adapt_learn_rate(self, epoch):
+        e = epoch - 1
+        if e < self.warmup:
+            lr = self.learn_rate * self.warmup_factor
+        elif e < 15:
+            lr = self.learn_rate
+        elif e < 20:
+            lr = self.learn_rate * self.learn_decay
+        elif e < 25:
+            lr = self.learn_rate * self.learn_decay ** 2
+        else:
+            lr = self.learn_rate * self.learn_decay ** 3
+        self.lr = lr
+        return lr
+
+    def to(self, image, device):
+        return image.to(device, non_blocking=True)      # the bf16 cast happens on device (ops.to_nhwc)
+
+    # ------------------------------------------------------------------ forward pieces
+    def vanilla_infer(self, in_image, i_batch=0, ret_last=False):
+        out = self.model(in_image)
+        cam_feat, last_feat = (out, None) if self.legacy else out
+        if self.legacy and isinstance(cam_feat, tuple):
+            cam_feat = cam_feat[0]
+        return (cam_feat, last_feat) if ret_last else cam_feat
+
+    def fusion_infer(self, color_image, depth_image, i_batch=0, ret_last=False):
+        cam_feat, last_feat = self.model(color_image, depth_image)
+        return (cam_feat, last_feat) if ret_last else cam_feat
+
+    def _forward_loss(self, color, depth, true_cam, true_val):
+        if self.do_fusion or getattr(self.model, "fused", False):
+            cam_feat = self.fusion_infer(color, depth)
+        else:
+            kind = getattr(self.model, "kind", "depthnet")
+            use_depth = kind == "partial_depthnet" or (kind == "depthnet" and self.depth_only)
+            cam_feat = self.vanilla_infer(depth if use_depth else color)
+        coords = utils.heatmap_coords(cam_feat, self.depth, self.num_joints, self.depth_range)
+        loss, spec = utils.pose_loss(coords, true_cam, true_val, self.key_index,
+                                     1.0 if self.legacy else self.loss_div, self.criterion)
+        return loss, spec
+
+    # ------------------------------------------------------------------ one optimisation step
+    def _fwd_bwd(self, batch):
+        self.flat.g.zero_()
+        loss, spec = self._forward_loss(*batch)
+        loss.backward()
+        return loss.detach(), spec
+
+    def _update(self):
+        f = self.flat
+        self.sumsq.zero_()
+        L.call("b2_grad_sumsq", L.ptr(f.g), f.n, L.ptr(self.sumsq), L.stream())
+        L.call("b2_adam_step", L.ptr(f.w), L.ptr(f.g), L.ptr(f.m), L.ptr(f.v), L.ptr(f.w16), f.n,
+               float(self.lr), self.betas[0], self.betas[1], self.eps, float(self.weight_decay), 1,
+               L.ptr(self.sumsq), float(self.grad_norm), 1.0 / self.world, L.ptr(self.hyper), L.stream())
+
+    def _set_hyper(self):
+        self.step_count += 1
+        t = self.step_count
+        self._hyper_host[0] = self.lr
+        self._hyper_host[1] = 1.0 - self.betas[0] ** t
+        self._hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** t)
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+
+    def _static_batch(self, batch):
+        key = tuple(tuple(t.shape) for t in batch)
+        st = self._static.get(key)
+        if st is None:
+            st = tuple(torch.empty(t.shape, dtype=(torch.uint8 if t.dtype == torch.bool else t.dtype),
+                                   device=self.device) for t in batch)
+            self._static[key] = st
+        for s, t in zip(st, batch):
+            s.copy_(t.view(torch.uint8) if t.dtype == torch.bool else t, non_blocking=True)
+        return key, st
+
+    def train_step(self, batch):
+        """One fwd + bwd + clip + Adam step on ``batch`` = (color, depth, true_cam, true_val)
+        (host or device tensors).  Returns dict(loss=0-dim tensor, spec_cam=[N,J,3], grad_norm)."""
+        self._set_hyper()
+        key, st = self._static_batch(batch)
+        dist_on = self.world > 1
+        n0 = L.launches
+        if not self.use_graph:
+            loss, spec = self._fwd_bwd(st)
+            if dist_on:
+                self.buckets.allreduce()
+            self._update()
+            self.launches_per_step = L.launches - n0
+        else:
+            entry = self._graphs.get(key)
+            if entry is None:
+                entry = self._capture(key, st)
+            if entry["stage"] < 3:               # eager warm-up iterations before capture
+                loss, spec = self._fwd_bwd(st)
+                if dist_on:
+                    self.buckets.allreduce()
+                self._update()
+                entry["stage"] += 1
+                if entry["stage"] == 3:
+                    self._do_capture(entry, st)
+            else:
+                entry["fb"].replay()
+                if dist_on:
+                    self.buckets.allreduce()
+                entry["up"].replay()
+                loss, spec = entry["loss"], entry["spec"]
+        if self.bns and self.model.training:
+            torch._foreach_add_([m.num_batches_tracked for m in self.bns if m.training], 1)
+        return dict(loss=loss, spec_cam=spec, grad_sumsq=self.sumsq)
+
+    def _capture(self, key, st):
+        entry = dict(stage=0)
+        self._graphs[key] = entry
+        return entry
+
+    def _do_capture(self, entry, st):
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        n0 = L.launches
+        fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fb, pool=pool):
+            loss, spec = self._fwd_bwd(st)
+        up = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(up, pool=pool):
+            self._update()
+        entry.update(fb=fb, up=up, loss=loss, spec=spec)
+        self.launches_per_step = L.launches - n0     # libb2pose kernels recorded into the two graphs
+        # the capture itself did not execute: the grads in the flat buffer are from the last eager
+        # warm-up step and have been consumed already, nothing to redo.
+
+    # ------------------------------------------------------------------ epoch loops (reference API)
+    def _epoch(self, epoch, data_loader, device):
+        n_batches = len(data_loader)
+        loss_avg, total = 0.0, 0
+        for i_batch, batch in enumerate(data_loader):
+            out = self.train_step(tuple(batch))
+            n = batch[2].size(0)
+            val = out["loss"].item()
+            print("| train Epoch[%d] [%d/%d]  Loss %1.4f" % (epoch, i_batch, n_batches, val), flush=True)
+            loss_avg += val * n
+            total += n
+        loss_avg /= max(total, 1)
+        print("\n=> train Epoch[%d]  Cam Loss: %1.4f\n" % (epoch, loss_avg))
+        return dict(cam_train_loss=loss_avg)
+
+    def vanilla_train(self, epoch, data_loader, device=None):
+        return self._epoch(epoch, data_loader, device)
+
+    def fusion_train(self, epoch, data_loader, device=None):
+        return self._epoch(epoch, data_loader, device)
+
+    cam_train = vanilla_train        # train.py:145-192 (legacy RGB loop; same head + loss)
+
+    def train(self, epoch, data_loader):
+        self.model.train()
+        self.adapt_learn_rate(epoch)
+        if self.do_fusion:
+            return self.fusion_train(epoch, data_loader, self.device)
+        return self.vanilla_train(epoch, data_loader, self.device)
+
+    @torch.no_grad()
+    def predict(self, batch):
+        """Eval-mode forward + head: returns (spec_cam [N,J,3], loss) like the *_test loops' core."""
+        was = self.model.training
+        self.model.eval()
+        try:
+            batch = tuple(t.to(self.device) for t in batch)
+            loss, spec = self._forward_loss(batch[0], batch[1], batch[2],
+                                            batch[3].view(torch.uint8) if batch[3].dtype == torch.bool else batch[3])
+        finally:
+            self.model.train(was)
+        return spec, loss

@@ -1,0 +1,202 @@
+/*
+ * b2pose.h -- C ABI of the B200-native depth-stream hot path.
+ *
+ * The reference (Hunger-Prevails/3D-Pose-Estimation-with-Previleged-Information) has no
+ * FFI / plugin / operator registry: its boundary is a Python module surface built on ATen
+ * calls.  Each entry point below therefore names the reference
+ * Python interface whose device work it replaces (file:line under /root/reference).  The
+ * Python host layer (package dir "3d-pose-estimation-with-previleged-information_b200")
+ * binds these with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller; the library never allocates,
+ *    frees or synchronises; all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *  - activations are NHWC ("channels_last"), filters KRSC, masks [N,H,W] fp32 in {0,1}.
+ *  - `dtype` selects the activation/filter element type: B2_F32 (CUDA-core FFMA path, used
+ *    for the fp32 parity mode) or B2_BF16 (tcgen05 tensor-core path, fp32 accumulate).
+ *  - return value: 0 on success, negative B2_E* otherwise; b2_last_error() gives a
+ *    thread-local message.  There is no CPU fallback anywhere.
+ */
+#ifndef B2POSE_H_
+#define B2POSE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 1
+
+enum { B2_F32 = 0, B2_BF16 = 1 };
+
+enum {
+  B2_OK = 0,
+  B2_E_BADARG = -1,      /* null pointer / inconsistent shape */
+  B2_E_UNSUPPORTED = -2, /* configuration this build has no kernel for */
+  B2_E_LAUNCH = -3,      /* CUDA launch / runtime failure */
+  B2_E_WORKSPACE = -4    /* workspace too small */
+};
+
+/* conv flags */
+enum {
+  B2_CONV_PARTIAL = 1,       /* mask-renormalised (PartialConv) semantics                      */
+  B2_CONV_X_PREMASKED = 2,   /* caller guarantees x == x*mask_in (skip the multiply)           */
+  B2_CONV_DY_PRESCALED = 4,  /* dgrad/wgrad: dy already multiplied by `ratio`                  */
+  B2_CONV_FORCE_FFMA = 8,    /* debugging / fp32-accurate path even for bf16 tensors           */
+  B2_CONV_RELU_IN = 16       /* reserved                                                       */
+};
+
+typedef struct B2ConvDesc {
+  int32_t N, H, W, C;        /* input  x : [N,H,W,C]                                            */
+  int32_t K, R, S;           /* filter w : [K,R,S,C]                                            */
+  int32_t stride, pad, dil;  /* same in both spatial dims (all reference layers are square)     */
+  int32_t Ho, Wo;            /* output y : [N,Ho,Wo,K]                                          */
+  int32_t dtype;             /* B2_F32 | B2_BF16 for x, w, y, dy, dx                            */
+  int32_t flags;             /* B2_CONV_*                                                       */
+} B2ConvDesc;
+
+int b2_abi_version(void);
+const char* b2_last_error(void);
+/* 1 if the bf16 tensor-core (tcgen05) kernel will be used for this descriptor and op
+ * (0 = fprop, 1 = dgrad, 2 = wgrad), 0 if the FFMA kernel will. */
+int b2_conv_uses_tensor_cores(const B2ConvDesc* d, int op);
+/* bytes of scratch the call may need (0 for most configurations). */
+size_t b2_conv_workspace_bytes(const B2ConvDesc* d, int op);
+
+/* ---- partial convolution --------------------------------------------------------------
+ * replaces PartialConv.forward, partial_conv.py:32-58 (and plain nn.Conv2d.forward when
+ * B2_CONV_PARTIAL is clear: partial_depthnet.py:201, fusionnet.py:136, ...).
+ *   mask_out[n,oh,ow] = clamp(sum_window mask_in, 0, 1)                      (:39,:43)
+ *   ratio            = (R*S)/(sum + 1e-6) * mask_out   (fp32)                (:41,:44)
+ *   y = conv(x*mask_in, w) * ratio                      (no bias, :53)
+ *   y = (conv(x*mask_in, w) * ratio + bias) * mask_out  (bias, :49-51)
+ * mask_in/mask_out/ratio_out are fp32; ratio_out (optional) saves the per-pixel factor for
+ * the backward pass.  bias is fp32 [K] or NULL.  bn_sums (optional, double[2*K], caller
+ * zeroes) receives per-channel sum / sum-of-squares of the stored y for training BatchNorm. */
+int b2_pconv_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, const void* w,
+                   const float* bias, void* y, float* mask_out, float* ratio_out, double* bn_sums,
+                   void* workspace, size_t ws_bytes, void* stream);
+
+/* backward of the above w.r.t. x (autograd of partial_conv.py:46-53):
+ *   dx = dgrad(w, dy * ratio) * mask_in
+ * ratio / mask_in may be NULL (plain convolution). */
+int b2_pconv_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w,
+                   const float* mask_in, void* dx, void* workspace, size_t ws_bytes, void* stream);
+
+/* backward w.r.t. w:  dw[K,R,S,C] (fp32, ACCUMULATED into) += wgrad(x*mask_in, dy*ratio). */
+int b2_pconv_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy,
+                   const float* ratio, float* dw, void* workspace, size_t ws_bytes, void* stream);
+
+/* only the mask algebra (partial_conv.py:39-44), for callers that need the veil without a conv. */
+int b2_pconv_mask_update(const B2ConvDesc* d, const float* mask_in, float* mask_out, float* ratio_out,
+                         void* stream);
+
+/* ---- row / column helpers (NHWC activations viewed as [rows, C]) ---------------------- */
+/* out[r,c] = in[r,c] * scale[r]   (scale fp32) */
+int b2_scale_rows(const void* in, const float* scale, void* out, int64_t rows, int32_t C, int32_t dtype,
+                  void* stream);
+/* sums[c] += sum_r in[r,c] * (w ? w[r] : 1)   (fp32 accumulate into sums[C]) -- bias gradients */
+int b2_col_sum(const void* in, const float* row_weight, float* sums, int64_t rows, int32_t C, int32_t dtype,
+               void* stream);
+/* veil = (depth != 0)  : partial_depthnet.py:215, partial_fusionnet.py:255 */
+int b2_veil_from_depth(const void* depth, float* veil, int64_t n, int32_t dtype, void* stream);
+/* NCHW fp32 -> NHWC dtype (host batches arrive NCHW fp32: depth_train.py:386) and back */
+int b2_nchw_to_nhwc(const float* in, void* out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t dtype,
+                    void* stream);
+int b2_nhwc_to_nchw(const void* in, float* out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t dtype,
+                    void* stream);
+/* dst = (dtype) src, elementwise fp32 -> bf16 (weight shadow copies) */
+int b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- BatchNorm2d (+ReLU, +residual, +veil) --------------------------------------------
+ * replaces nn.BatchNorm2d / F.relu / residual add in the blocks, partial_depthnet.py:143-157,
+ * fusionnet.py:107-127,138-140.  Training statistics are per call (per rank), momentum
+ * update of running stats as torch (unbiased variance). */
+/* sums[0:C] += sum_r y, sums[C:2C] += sum_r y^2  (double) */
+int b2_bn_stats(const void* y, int64_t rows, int32_t C, int32_t dtype, double* sums, void* stream);
+/* z = relu?( (y-mean)*invstd*gamma + beta (+ residual) ) (* row_mask[r])
+ * training != 0: mean/var from `sums` (count = rows), running stats updated, save_mean /
+ * save_invstd written; training == 0: mean/var from running stats. */
+int b2_bn_apply(const void* y, const double* sums, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, float momentum, float eps, int32_t training,
+                const void* residual, const float* row_mask, int32_t relu, void* z, float* save_mean,
+                float* save_invstd, int64_t rows, int32_t C, int32_t dtype, void* stream);
+/* backward, pass 1: g = dz * (relu ? z>0 : 1) (* row_mask);  sums[0:C] += sum g,
+ * sums[C:2C] += sum g * xhat. */
+int b2_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
+                     const float* row_mask, int32_t relu, double* sums, int64_t rows, int32_t C,
+                     int32_t dtype, void* stream);
+/* backward, pass 2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) (* row_scale[r]);
+ * d_residual = g (optional); dgamma += sum g*xhat, dbeta += sum g (fp32, accumulated).
+ * training == 0 (frozen statistics): dy = gamma*invstd*g. */
+int b2_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
+                    const float* gamma, const double* sums, const float* row_mask, const float* row_scale,
+                    int32_t relu, int32_t training, void* dy, void* d_residual, float* dgamma, float* dbeta,
+                    int64_t rows, int32_t C, int32_t dtype, void* stream);
+
+/* ---- MaxPool2d(3, stride 2, pad 1) on x and veil together: partial_depthnet.py:219-220 --- */
+int b2_maxpool3x3s2_fwd(const void* x, const float* veil_in, void* y, uint8_t* argmax, float* veil_out,
+                        int32_t N, int32_t H, int32_t W, int32_t C, int32_t dtype, void* stream);
+int b2_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* dx, int32_t N, int32_t H, int32_t W,
+                        int32_t C, int32_t dtype, void* stream);
+
+/* ---- volumetric heat-map head ----------------------------------------------------------
+ * replaces utils.to_heatmap + utils.decode, utils.py:154-194, in one pass.
+ * logits: channel index = d*J + j;  layout 0 = NHWC [N,H,W,D*J], 1 = NCHW [N,D*J,H,W].
+ * coords [N,J,3] = (x<-W, y<-H, z<-D) * depth_range; vmax/vsum [N,J] saved for backward. */
+int b2_head_fwd(const void* logits, int32_t N, int32_t J, int32_t D, int32_t H, int32_t W, int32_t layout,
+                int32_t dtype, float depth_range, float* coords, float* vmax, float* vsum, void* stream);
+/* dlogit_i = p_i * (u . g_i - u . c),  u = dcoords, g_i = grid coords of voxel i (x depth_range) */
+int b2_head_bwd(const void* logits, const float* dcoords, const float* coords, const float* vmax,
+                const float* vsum, int32_t N, int32_t J, int32_t D, int32_t H, int32_t W, int32_t layout,
+                int32_t dtype, float depth_range, void* dlogits, void* stream);
+/* materialised heat-map for API compatibility: heat [N,J,H,W,D] fp32 (utils.py:154-175);
+ * coords_scratch: [N,J,3] floats of scratch. */
+int b2_heatmap_softmax(const void* logits, int32_t N, int32_t J, int32_t D, int32_t H, int32_t W,
+                       int32_t layout, int32_t dtype, float* heat, float* coords_scratch, void* stream);
+/* utils.decode on a materialised heat-map (utils.py:178-194) and its backward */
+int b2_heatmap_decode(const float* heat, int32_t N, int32_t J, int32_t D, int32_t H, int32_t W,
+                      float depth_range, float* coords, void* stream);
+int b2_heatmap_decode_bwd(const float* dcoords, int32_t N, int32_t J, int32_t D, int32_t H, int32_t W,
+                          float depth_range, float* dheat, void* stream);
+/* softmax backward on the materialised heat-map: dlogits = p*(dp - sum p*dp), written in `layout` */
+int b2_heatmap_softmax_bwd(const float* heat, const float* dheat, int32_t N, int32_t J, int32_t D, int32_t H,
+                           int32_t W, int32_t layout, int32_t dtype, void* dlogits, void* stream);
+
+/* root-relative shift + masked SmoothL1/L1/MSE (mean) and its gradient: depth_train.py:397-405.
+ * criterion 0 = SmoothL1(beta 1), 1 = L1, 2 = MSE.  valid: uint8 [N,J].
+ * out: loss[1], spec_cam [N,J,3], dcoords [N,J,3] = d loss / d coords. */
+int b2_pose_loss(const float* coords, const float* true_cam, const uint8_t* valid, int32_t N, int32_t J,
+                 int32_t key_index, float loss_div, int32_t criterion, float* loss, float* spec_cam,
+                 float* dcoords, void* stream);
+
+/* ---- depth unprojection: utils.to_depth (utils.py:68-75) + Camera.image_to_camera
+ * (cameralib.py:188-200, no-distortion branch).  kinv = inv(K[:2,:2]) row-major, c = K[:2,2].
+ * out = img / sqrt(xn^2 + yn^2 + 2), (xn,yn) = ((u,v) - c) @ kinv^T, fp32.  n_img images. */
+int b2_unproject_depth(const float* img, float* out, int32_t n_img, int32_t H, int32_t W, const float kinv[4],
+                       const float c[2], void* stream);
+
+/* ---- optimizer: clip_grad_norm_ + Adam (L2 weight decay), depth_train.py:451-456 ---------
+ * sumsq (double[1], caller zeroes) += sum g^2 */
+int b2_grad_sumsq(const float* g, int64_t n, double* sumsq, void* stream);
+/* one fused step over flat fp32 buffers.  coef = min(1, max_norm/(sqrt(sumsq)*inv_scale + 1e-6));
+ * g' = g*inv_scale*coef + wd*w; Adam(m, v) with bias correction from `step` (1-based);
+ * the whole update is skipped when sumsq is not finite (the reference's inf-skip, :435-438).
+ * w16 (optional) receives the bf16 shadow of the new weights.
+ * dev_hyper (optional, DEVICE float[3] = {lr, 1-beta1^step, sqrt(1-beta2^step)}) overrides the
+ * by-value lr/step so that a captured CUDA graph of the step can be replayed with a moving step
+ * count and learning-rate schedule (depth_train.py:621-638). */
+int b2_adam_step(float* w, const float* g, float* m, float* v, void* w16, int64_t n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int32_t step, const double* sumsq,
+                 float max_norm, float inv_scale, const float* dev_hyper, void* stream);
+
+/* ---- debug: tcgen05 descriptor self-test (used by tests/test_tc_selftest.py) ------------- */
+int b2_tc_selftest(const void* a, const void* b, float* c, int32_t M, int32_t N, int32_t K, int32_t variant,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2POSE_H_ */

@@ -6,6 +6,7 @@ valid Python identifier, so ``__graft_entry__.load_package()`` registers it as `
 import os
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,9 +21,29 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def b2pose():
     import __graft_entry__ as ge
+    if not os.path.exists(ge.LIB):
+        ge.build()
     return ge.load_package()
 
 
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def dev():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b|  -- the 'relative' of BASELINE.json's tolerances."""
+    import torch
+    if torch.is_tensor(a):
+        a = a.detach().float().cpu().numpy()
+    if torch.is_tensor(b):
+        b = b.detach().float().cpu().numpy()
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
