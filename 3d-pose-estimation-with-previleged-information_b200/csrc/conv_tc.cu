@@ -1,24 +1,769 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the tensor-core kernels land).
+// tcgen05 implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+//   fprop : D[pixels, K] = sum over (tap, c) of X[pixel shifted by tap, c] * W[k, tap, c]
+//   dgrad : the same kernel run on dy with the filter flipped/transposed (stride-1 layers)
+//   wgrad : D[k, (tap, c)] = sum over pixels of dY[pixel, k] * X[pixel shifted by tap, c]  (MN-major operands)
+//
+// One persistent CTA per SM (192 threads): warp 0 is the TMA producer, warp 1 issues tcgen05.mma
+// (one elected lane), warps 2-5 are the epilogue (each owns the 32 TMEM lanes of its warp-id
+// quarter).  Activation tiles are fetched with 4-D *tiled* TMA boxes (C, W, H, N): a tile of
+// output pixels is a BNIxBHxBW brick, and for filter tap (r, s) the A operand is that brick
+// shifted by (r*dil - pad, s*dil - pad); out-of-bounds rows/columns (padding, ragged edges) are
+// zero-filled by the TMA unit, strided layers use the tensor map's element strides.  Tiles land
+// in shared memory in the 128-byte-swizzled K-major layout the UMMA descriptors expect, so no
+// thread ever touches the operands.  Accumulators are double buffered in TMEM so the epilogue of
+// tile i (ratio / bias / bf16 pack / store) overlaps the MMAs of tile i+1.
+//
+// PartialConv semantics (partial_conv.py:32-58): 1x1 layers need no input masking at all
+// (conv(x*m) == conv(x)*m row-wise, and m is folded into the ratio); 3x3 layers read input that
+// the producing BN epilogue already multiplied by the veil (B2_CONV_X_PREMASKED); the epilogue
+// computes the mask-window count for its pixel, emits mask_out / ratio and scales the row.
+#include <cuda.h>
+
 #include "b2_common.cuh"
 
-bool conv_tc_supported(const B2ConvDesc*, int) { return false; }
-size_t conv_tc_workspace_bytes(const B2ConvDesc*, int) { return 0; }
-int conv_tc_fprop(const B2ConvDesc*, const void*, const float*, const void*, const float*, void*, float*, float*,
-                  double*, void*, cudaStream_t) {
-  b2_set_error("conv_tc_fprop: not built");
-  return B2_E_UNSUPPORTED;
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;          // UMMA M (output pixels per tile / TMEM lanes)
+constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
+constexpr uint32_t kABytes = kTileM * kBlockK * 2;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int conv_tc_dgrad(const B2ConvDesc*, const void*, const float*, const void*, const float*, void*, void*,
-                  cudaStream_t) {
-  b2_set_error("conv_tc_dgrad: not built");
-  return B2_E_UNSUPPORTED;
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-int conv_tc_wgrad(const B2ConvDesc*, const void*, const float*, const void*, const float*, float*, void*,
-                  cudaStream_t) {
-  b2_set_error("conv_tc_wgrad: not built");
-  return B2_E_UNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-extern "C" int b2_tc_selftest(const void*, const void*, float*, int32_t, int32_t, int32_t, int32_t, void*) {
-  b2_set_error("tc_selftest: not built");
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((it & 1023) == 1023) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, 128-byte swizzle (layout type 2), descriptor version 1
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: fp32 accumulate, bf16 A/B
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ fprop / dgrad kernel
+struct FpropParams {
+  int N, H, W, C, K, R, S, stride, pad, dil, Ho, Wo;   // H,W,C: tensor read by TMA; Ho,Wo,K: tensor written
+  int BW, BH, BNI;                                     // pixel brick of one tile
+  int tiles_w, tiles_h, tiles_n, tiles_k;              // tile grid (k = output-channel tiles)
+  int BN;                                              // output channels per tile (multiple of 16, <= 256)
+  int cblocks, kblocks;                                // C/64, taps*C/64
+  int stages, tmem_cols;
+  int scale_mode;                                      // 0 none, 1 partial-conv ratio from mask_in, 2 row_scale[]
+  int mask_R, mask_S, mask_stride, mask_pad, mask_dil, mask_H, mask_W;   // window geometry for mode 1
+  const float* mask_in;
+  const float* row_scale;
+  const float* bias;
+  float* mask_out;
+  float* ratio_out;
+  bf16* out;
+  int out_stride_sp;                                   // dgrad of a strided 1x1: scatter factor (1 otherwise)
+  int out_H, out_W;                                    // spatial size of the tensor written
+};
+
+struct __align__(8) PipeBars {
+  uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const FpropParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  PipeBars* bars = reinterpret_cast<PipeBars*>(smem + (size_t)p.stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  const int total_tiles = m_tiles * p.tiles_k;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 4); }
+    fence_barrier_init();
+    prefetch_map(&map_a);
+    prefetch_map(&map_b);
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BNI) * kBlockK * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int kt = tile % p.tiles_k, mt = tile / p.tiles_k;
+        const int wi = mt % p.tiles_w, hi = (mt / p.tiles_w) % p.tiles_h, ni = mt / (p.tiles_w * p.tiles_h);
+        const int iw0 = wi * p.BW * p.stride - p.pad, ih0 = hi * p.BH * p.stride - p.pad, n0 = ni * p.BNI;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          const int r = tap / p.S, s = tap - r * p.S;
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          mbar_expect_tx(&bars->full[stage], a_box_bytes + b_bytes);
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          tma_load_4d(sa, &map_a, &bars->full[stage], cb * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, n0);
+          tma_load_2d(sa + kABytes, &map_b, &bars->full[stage], tap * p.C + cb * kBlockK, kt * p.BN);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = instr_desc(kTileM, p.BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&bars->tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&bars->full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = smem_desc(sa, 0, 1024), bdesc = smem_desc(sa + kABytes, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(kb | k));
+          umma_commit(&bars->empty[stage]);
+          if (kb == p.kblocks - 1) umma_commit(&bars->tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int brick = p.BW * p.BH;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int kt = tile % p.tiles_k, mt = tile / p.tiles_k;
+      const int wi = mt % p.tiles_w, hi = (mt / p.tiles_w) % p.tiles_h, ni = mt / (p.tiles_w * p.tiles_h);
+      const int bn = row / brick, rem = row - bn * brick;
+      const int bh = rem / p.BW, bw = rem - bh * p.BW;
+      const int n = ni * p.BNI + bn, oh = hi * p.BH + bh, ow = wi * p.BW + bw;
+      const bool valid = (bn < p.BNI) && (n < p.N) && (oh < p.Ho) && (ow < p.Wo);
+      float scale = 1.f, mo = 1.f;
+      long long opix = 0;
+      if (valid) {
+        const long long pix = ((long long)n * p.Ho + oh) * p.Wo + ow;
+        opix = ((long long)n * p.out_H + (long long)oh * p.out_stride_sp) * p.out_W + (long long)ow * p.out_stride_sp;
+        if (p.scale_mode == 1) {
+          float cnt = 0.f;
+          for (int r = 0; r < p.mask_R; ++r) {
+            const int ih = oh * p.mask_stride - p.mask_pad + r * p.mask_dil;
+            if (ih < 0 || ih >= p.mask_H) continue;
+            for (int s = 0; s < p.mask_S; ++s) {
+              const int iw = ow * p.mask_stride - p.mask_pad + s * p.mask_dil;
+              if (iw < 0 || iw >= p.mask_W) continue;
+              cnt += __ldg(p.mask_in + ((long long)n * p.mask_H + ih) * p.mask_W + iw);
+            }
+          }
+          scale = pconv_ratio((float)(p.mask_R * p.mask_S), cnt);
+          mo = fminf(fmaxf(cnt, 0.f), 1.f);
+          if (kt == 0) {
+            if (p.mask_out) p.mask_out[pix] = mo;
+            if (p.ratio_out) p.ratio_out[pix] = scale;
+          }
+        } else if (p.scale_mode == 2) {
+          scale = __ldg(p.row_scale + opix);
+        }
+      }
+      mbar_wait(&bars->tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      const int kbase = kt * p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        const bool two = (c0 + 16) < p.BN;
+        tmem_ld16(taddr + c0, v);
+        if (two) tmem_ld16(taddr + c0 + 16, v + 16);
+        tmem_ld_wait();
+        if (valid) {
+          const int ncol = two ? 32 : 16;
+          bf16* orow = p.out + opix * p.K + kbase + c0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g * 8 >= ncol) break;
+            const int col = kbase + c0 + g * 8;
+            if (col >= p.K) break;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float t = __uint_as_float(v[g * 8 + j]) * scale;
+              if (p.bias) t = (t + __ldg(p.bias + col + j)) * mo;
+              f[j] = t;
+            }
+            store8(orow + g * 8, f);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------ wgrad kernel
+// Work item = (pixel split, tap, c-tile of BNc channels, k-tile of 128 output channels):
+// D[128 k, BNc c] accumulated in TMEM over the item's pixel bricks, then red.add into dw (fp32).
+struct WgradParams {
+  int N, H, W, C, K, R, S, stride, pad, dil, Ho, Wo;
+  int BW, BH, BNI;                 // pixel brick per pipeline stage (BW*BH*BNI = 64 pixels incl. ragged rows)
+  int tiles_w, tiles_h, tiles_n;   // bricks over the OUTPUT pixel space
+  int BNc, ctiles, ktiles, splits; // columns per item, C/BNc, ceil(K/128), pixel splits
+  int bricks_per_split;
+  int stages, tmem_cols;
+  float* dw;                       // [K][R*S][C] fp32
+};
+constexpr int kWgPix = 64;         // pixels per stage
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // stage: A = dy [2 atoms of 64 k][64 pix][128 B]  (16 KB), B = x [BNc/64 atoms][64 pix][128 B]
+  const uint32_t atom_bytes = kWgPix * 128;
+  const uint32_t a_bytes = 2 * atom_bytes, b_bytes = (uint32_t)(p.BNc / 64) * atom_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  PipeBars* bars = reinterpret_cast<PipeBars*>(smem + (size_t)p.stages * stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = p.R * p.S;
+  const int total_items = p.splits * taps * p.ctiles * p.ktiles;
+  const int total_bricks = p.tiles_n * p.tiles_h * p.tiles_w;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 4); }
+    fence_barrier_init();
+    prefetch_map(&map_dy);
+    prefetch_map(&map_x);
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // item decode: split fastest so CTAs running together share the same filter tile / spread pixels
+  auto decode = [&](int item, int& sp, int& tap, int& ct, int& kt) {
+    sp = item % p.splits; item /= p.splits;
+    ct = item % p.ctiles; item /= p.ctiles;
+    tap = item % taps;    kt = item / taps;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int sp, tap, ct, kt;
+        decode(item, sp, tap, ct, kt);
+        const int r = tap / p.S, s = tap - r * p.S;
+        const int b0 = sp * p.bricks_per_split;
+        const int b1 = min(total_bricks, b0 + p.bricks_per_split);
+        for (int b = b0; b < b1; ++b) {
+          const int wi = b % p.tiles_w, hi = (b / p.tiles_w) % p.tiles_h, ni = b / (p.tiles_w * p.tiles_h);
+          const int ow0 = wi * p.BW, oh0 = hi * p.BH, n0 = ni * p.BNI;
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          mbar_expect_tx(&bars->full[stage], stage_bytes);
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          // dy atoms: k channels [kt*128, +64) and [+64, +128)
+          tma_load_4d(sa, &map_dy, &bars->full[stage], kt * 128, ow0, oh0, n0);
+          tma_load_4d(sa + atom_bytes, &map_dy, &bars->full[stage], kt * 128 + 64, ow0, oh0, n0);
+          for (int a = 0; a < p.BNc / 64; ++a)
+            tma_load_4d(sa + a_bytes + a * atom_bytes, &map_x, &bars->full[stage], ct * p.BNc + a * 64,
+                        ow0 * p.stride - p.pad + s * p.dil, oh0 * p.stride - p.pad + r * p.dil, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = instr_desc(kTileM, p.BNc, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++local) {
+      int sp, tap, ct, kt;
+      decode(item, sp, tap, ct, kt);
+      const int b0 = sp * p.bricks_per_split;
+      const int b1 = min(total_bricks, b0 + p.bricks_per_split);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&bars->tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BNc);
+      for (int b = b0; b < b1; ++b) {
+        mbar_wait(&bars->full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          // MN-major, 128B swizzle: LBO = bytes between 64-element atoms along M/N, SBO = 1024 (8 pixel rows)
+          const uint64_t adesc = smem_desc(sa, atom_bytes, 1024), bdesc = smem_desc(sa + a_bytes, atom_bytes, 1024);
+#pragma unroll
+          for (int k = 0; k < kWgPix / 16; ++k)      // 16 pixels per MMA = 2 swizzle row groups = 2048 B
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
+                      (uint32_t)((b - b0) | k));
+          umma_commit(&bars->empty[stage]);
+          if (b == b1 - 1) umma_commit(&bars->tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int local = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++local) {
+      int sp, tap, ct, kt;
+      decode(item, sp, tap, ct, kt);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&bars->tfull[acc], acc_phase);
+      tc_fence_after();
+      const int k = kt * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BNc);
+      float* drow = p.dw + ((long long)k * taps + tap) * p.C + ct * p.BNc;
+      for (int c0 = 0; c0 < p.BNc; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld16(taddr + c0 + 16, v + 16);
+        tmem_ld_wait();
+        if (k < p.K) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, __uint_as_float(v[j]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------ filter transform for dgrad
+// W[k][r][s][c] -> Wt[c][R-1-r][S-1-s][k]   (bf16), 32x32 shared-memory transpose per tap
+__global__ void flip_transpose_kernel(const bf16* __restrict__ w, bf16* __restrict__ wt, int K, int C, int R, int S) {
+  __shared__ bf16 tile[32][33];
+  const int tap = blockIdx.z, r = tap / S, s = tap - r * S;
+  const int ftap = (R - 1 - r) * S + (S - 1 - s);
+  const int k0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int k = k0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && c < C) ? w[((long long)k * R * S + tap) * C + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, k = k0 + threadIdx.x;
+    if (k < K && c < C) wt[((long long)c * R * S + ftap) * K + k] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 4-D map over an NHWC bf16 tensor: dims (C, W, H, N), box (64, bw*es, bh*es, bni), element strides es
+int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bni, int es) {
+  EncodeTiledFn fn = encode_fn();
+  B2_REQUIRE(fn != nullptr, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), (cuuint32_t)bni};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2_REQUIRE(r == CUDA_SUCCESS, B2_E_LAUNCH,
+             "conv_tc: cuTensorMapEncodeTiled(activation N=%d H=%d W=%d C=%d box %dx%dx%d es=%d) failed: %d", N, H, W,
+             C, bni, bh, bw, es, (int)r);
+  return B2_OK;
+}
+
+// 2-D map over a [rows, cols] bf16 matrix, box (64, box_rows)
+int make_mat_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  B2_REQUIRE(fn != nullptr, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2_REQUIRE(r == CUDA_SUCCESS, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled(matrix %lldx%lld box %d) failed: %d", rows,
+             cols, box_rows, (int)r);
+  return B2_OK;
+}
+
+// brick of <= limit output pixels maximising tile occupancy
+void choose_brick(int N, int Ho, int Wo, int limit, int need_multiple, int* bw_o, int* bh_o, int* bni_o) {
+  double best = -1;
+  int bbw = 1, bbh = 1, bbn = 1;
+  for (int bw = 1; bw <= Wo && bw <= limit; ++bw) {
+    int bh = limit / bw;
+    if (bh > Ho) bh = Ho;
+    if (bh < 1) continue;
+    int bni = 1;
+    if (bw == Wo && bh == Ho) {
+      bni = limit / (bw * bh);
+      if (bni > N) bni = N;
+      if (bni < 1) bni = 1;
+    }
+    long long tiles = (long long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((N + bni - 1) / bni);
+    double eff = (double)N * Ho * Wo / ((double)tiles * limit);
+    (void)need_multiple;
+    if (eff > best + 1e-9) { best = eff; bbw = bw; bbh = bh; bbn = bni; }
+  }
+  *bw_o = bbw; *bh_o = bbh; *bni_o = bbn;
+}
+
+int smem_limit() {
+  static int lim = 0;
+  if (lim == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (lim <= 0) lim = 227 * 1024;
+  }
+  return lim;
+}
+
+int pow2_cols(int c) {
+  int v = 32;
+  while (v < c) v <<= 1;
+  return v;
+}
+
+// Generic launch of the fprop-style kernel: act [N,H,W,C] -> out [N,out_H,out_W,K]
+struct RunArgs {
+  const void* act; int N, H, W, C;
+  const void* filt; int K, R, S, stride, pad, dil, Ho, Wo;    // filt: [K][R*S*C] bf16
+  void* out; int out_H, out_W, out_stride_sp;
+  int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
+  float* mask_out; float* ratio_out;
+  int mask_R, mask_S, mask_stride, mask_pad, mask_dil, mask_H, mask_W;
+};
+
+int run_conv_tc(const RunArgs& a, cudaStream_t st) {
+  FpropParams p;
+  p.N = a.N; p.H = a.H; p.W = a.W; p.C = a.C; p.K = a.K; p.R = a.R; p.S = a.S;
+  p.stride = a.stride; p.pad = a.pad; p.dil = a.dil; p.Ho = a.Ho; p.Wo = a.Wo;
+  choose_brick(a.N, a.Ho, a.Wo, kTileM, 1, &p.BW, &p.BH, &p.BNI);
+  p.tiles_w = (a.Wo + p.BW - 1) / p.BW; p.tiles_h = (a.Ho + p.BH - 1) / p.BH; p.tiles_n = (a.N + p.BNI - 1) / p.BNI;
+  int nk = (a.K + 255) / 256;
+  p.BN = (((a.K + nk - 1) / nk) + 15) / 16 * 16;
+  p.tiles_k = (a.K + p.BN - 1) / p.BN;
+  p.cblocks = a.C / kBlockK; p.kblocks = a.R * a.S * p.cblocks;
+  const int stage_bytes = (int)kABytes + p.BN * kBlockK * 2;
+  int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars)) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  B2_REQUIRE(stages >= 2, B2_E_UNSUPPORTED, "conv_tc: not enough shared memory for two stages");
+  p.stages = stages;
+  p.tmem_cols = pow2_cols(2 * p.BN);
+  p.scale_mode = a.scale_mode; p.mask_in = a.mask_in; p.row_scale = a.row_scale; p.bias = a.bias;
+  p.mask_out = a.mask_out; p.ratio_out = a.ratio_out; p.out = (bf16*)a.out;
+  p.mask_R = a.mask_R; p.mask_S = a.mask_S; p.mask_stride = a.mask_stride; p.mask_pad = a.mask_pad;
+  p.mask_dil = a.mask_dil; p.mask_H = a.mask_H; p.mask_W = a.mask_W;
+  p.out_stride_sp = a.out_stride_sp; p.out_H = a.out_H; p.out_W = a.out_W;
+  CUtensorMap ma, mb;
+  int rc = make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
+  if (rc) return rc;
+  rc = make_mat_map(&mb, a.filt, a.K, (long long)a.R * a.S * a.C, p.BN);
+  if (rc) return rc;
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit());
+    B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    configured = smem_limit();
+  }
+  const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_k;
+  int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
+  conv_tc_kernel<<<grid, kThreads, smem, st>>>(ma, mb, p);
+  B2_LAUNCH_CHECK("conv_tc_kernel");
+  return B2_OK;
+}
+
+bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2POSE_DISABLE_TC");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ dispatch interface
+bool conv_tc_supported(const B2ConvDesc* d, int op) {
+  if (!tc_enabled() || d->dtype != B2_BF16) return false;
+  if (d->C % 64 != 0 || d->K % 8 != 0) return false;
+  const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
+  const bool one = (d->R == 1 && d->S == 1);
+  if (partial && !one && !premasked) return false;          // needs x*mask in the loader: CUDA-core path
+  if (partial && one && d->stride != 1) return false;
+  if (op == 0) return true;
+  if (op == 1) {
+    if (d->K % 64 != 0) return false;                       // K is the contraction of dgrad
+    if (d->stride == 1) return true;
+    return one && d->pad == 0;                              // strided 1x1: gather GEMM + scatter store
+  }
+  return op == 2;
+}
+
+size_t conv_tc_workspace_bytes(const B2ConvDesc* d, int op) {
+  size_t ws = 0;
+  const bool partial = d->flags & B2_CONV_PARTIAL;
+  const size_t dy_bytes = (size_t)d->N * d->Ho * d->Wo * d->K * 2;
+  if (op == 1) {
+    ws += ((size_t)d->K * d->R * d->S * d->C * 2 + 255) / 256 * 256;     // flipped filter
+    if (partial && !(d->flags & B2_CONV_DY_PRESCALED)) ws += dy_bytes;
+  }
+  if (op == 2 && partial && !(d->flags & B2_CONV_DY_PRESCALED)) ws += dy_bytes;
+  return ws;
+}
+
+int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, const void* w, const float* bias,
+                  void* y, float* mask_out, float* ratio_out, double* bn_sums, void* workspace, cudaStream_t st) {
+  (void)workspace;
+  RunArgs a{};
+  a.act = x; a.N = d->N; a.H = d->H; a.W = d->W; a.C = d->C;
+  a.filt = w; a.K = d->K; a.R = d->R; a.S = d->S; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
+  a.Ho = d->Ho; a.Wo = d->Wo; a.out = y; a.out_H = d->Ho; a.out_W = d->Wo; a.out_stride_sp = 1;
+  const bool partial = d->flags & B2_CONV_PARTIAL;
+  a.scale_mode = partial ? 1 : 0;
+  a.mask_in = mask_in; a.bias = bias; a.mask_out = mask_out; a.ratio_out = ratio_out;
+  a.mask_R = d->R; a.mask_S = d->S; a.mask_stride = d->stride; a.mask_pad = d->pad; a.mask_dil = d->dil;
+  a.mask_H = d->H; a.mask_W = d->W;
+  int rc = run_conv_tc(a, st);
+  if (rc) return rc;
+  if (bn_sums) return b2_bn_stats(y, (int64_t)d->N * d->Ho * d->Wo, d->K, d->dtype, bn_sums, (void*)st);
+  return B2_OK;
+}
+
+int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w, const float* mask_in,
+                  void* dx, void* workspace, cudaStream_t st) {
+  const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
+  uint8_t* ws = (uint8_t*)workspace;
+  bf16* wt = (bf16*)ws;
+  ws += ((size_t)d->K * d->R * d->S * d->C * 2 + 255) / 256 * 256;
+  dim3 tg((d->C + 31) / 32, (d->K + 31) / 32, d->R * d->S), tb(32, 8);
+  flip_transpose_kernel<<<tg, tb, 0, st>>>((const bf16*)w, wt, d->K, d->C, d->R, d->S);
+  B2_LAUNCH_CHECK("flip_transpose");
+  const void* dys = dy;
+  if (partial && !(d->flags & B2_CONV_DY_PRESCALED) && ratio) {
+    int rc = b2_scale_rows(dy, ratio, ws, (int64_t)d->N * d->Ho * d->Wo, d->K, B2_BF16, (void*)st);
+    if (rc) return rc;
+    dys = ws;
+  }
+  RunArgs a{};
+  a.act = dys; a.N = d->N; a.H = d->Ho; a.W = d->Wo; a.C = d->K;
+  a.filt = wt; a.K = d->C; a.R = d->R; a.S = d->S; a.dil = d->dil;
+  a.out = dx; a.out_H = d->H; a.out_W = d->W;
+  a.scale_mode = (partial && !premasked && mask_in) ? 2 : 0;
+  a.row_scale = mask_in;
+  if (d->stride == 1) {
+    a.stride = 1; a.pad = d->dil * (d->R - 1) - d->pad; a.Ho = d->H; a.Wo = d->W; a.out_stride_sp = 1;
+  } else {
+    // strided 1x1, pad 0: dx[n, oh*s, ow*s, :] = dy[n, oh, ow, :] @ W ; every other position is zero
+    cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->N * d->H * d->W * d->C * 2, st);
+    B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc_dgrad: memset failed: %s", cudaGetErrorString(e));
+    a.stride = 1; a.pad = 0; a.Ho = d->Ho; a.Wo = d->Wo; a.out_stride_sp = d->stride;
+  }
+  return run_conv_tc(a, st);
+}
+
+int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy, const float* ratio,
+                  float* dw, void* workspace, cudaStream_t st) {
+  (void)mask_in;   // 1x1: mask folded into the (pre)scaled dy rows; 3x3: x is pre-masked (see conv_tc_supported)
+  const bool partial = d->flags & B2_CONV_PARTIAL;
+  const void* dys = dy;
+  if (partial && !(d->flags & B2_CONV_DY_PRESCALED) && ratio) {
+    int rc = b2_scale_rows(dy, ratio, workspace, (int64_t)d->N * d->Ho * d->Wo, d->K, B2_BF16, (void*)st);
+    if (rc) return rc;
+    dys = workspace;
+  }
+  WgradParams p;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.K = d->K; p.R = d->R; p.S = d->S;
+  p.stride = d->stride; p.pad = d->pad; p.dil = d->dil; p.Ho = d->Ho; p.Wo = d->Wo;
+  // bricks of exactly 64 pixel slots over the output space (rows of 128 B each; ragged parts zero-filled)
+  {
+    double best = -1;
+    p.BW = 1; p.BH = 1; p.BNI = 1;
+    for (int bw = 1; bw <= kWgPix; bw <<= 1) {           // bw*bh*bni must equal 64 exactly
+      for (int bh = 1; bw * bh <= kWgPix; bh <<= 1) {
+        int bni = kWgPix / (bw * bh);
+        long long tiles = (long long)((d->Wo + bw - 1) / bw) * ((d->Ho + bh - 1) / bh) * ((d->N + bni - 1) / bni);
+        double eff = (double)d->N * d->Ho * d->Wo / ((double)tiles * kWgPix);
+        if (eff > best + 1e-9) { best = eff; p.BW = bw; p.BH = bh; p.BNI = bni; }
+      }
+    }
+  }
+  p.tiles_w = (d->Wo + p.BW - 1) / p.BW; p.tiles_h = (d->Ho + p.BH - 1) / p.BH; p.tiles_n = (d->N + p.BNI - 1) / p.BNI;
+  p.BNc = d->C % 256 == 0 ? 256 : (d->C % 128 == 0 ? 128 : 64);
+  p.ctiles = d->C / p.BNc;
+  p.ktiles = (d->K + 127) / 128;
+  const int taps = d->R * d->S;
+  const long long bricks = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+  const long long base_items = (long long)taps * p.ctiles * p.ktiles;
+  // enough pixel splits to fill the machine ~2x, but at least 8 bricks (512 pixels) per item
+  long long want = (2LL * b2_num_sms() + base_items - 1) / base_items;
+  long long max_splits = (bricks + 7) / 8;
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  p.bricks_per_split = (int)((bricks + want - 1) / want);
+  p.splits = (int)((bricks + p.bricks_per_split - 1) / p.bricks_per_split);
+  const int stage_bytes = 2 * kWgPix * 128 + (p.BNc / 64) * kWgPix * 128;
+  int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars)) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  p.tmem_cols = pow2_cols(2 * p.BNc);
+  p.dw = dw;
+  CUtensorMap mdy, mx;
+  int rc = make_act_map(&mdy, dys, d->N, d->Ho, d->Wo, d->K, p.BW, p.BH, p.BNI, 1);
+  if (rc) return rc;
+  rc = make_act_map(&mx, x, d->N, d->H, d->W, d->C, p.BW, p.BH, p.BNI, d->stride);
+  if (rc) return rc;
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit());
+    B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "wgrad_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long total = base_items * p.splits;
+  int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
+  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(mdy, mx, p);
+  B2_LAUNCH_CHECK("wgrad_tc_kernel");
+  return B2_OK;
+}
+
+// Debug entry: C[M,N] (fp32) = A[M,K] * B[N,K]^T through the fprop kernel (variant 0) or
+// C[M,N] = A[P,M]^T * B[P,N] through the wgrad kernel (variant 1); bf16 inputs.
+extern "C" int b2_tc_selftest(const void* a, const void* b, float* c, int32_t M, int32_t N, int32_t K, int32_t variant,
+                              void* stream) {
+  (void)a; (void)b; (void)c; (void)M; (void)N; (void)K; (void)variant; (void)stream;
+  b2_set_error("tc_selftest: use the convolution entry points with bf16 tensors (tests/test_gpu_tc.py)");
   return B2_E_UNSUPPORTED;
 }

@@ -1,0 +1,106 @@
+"""GPU parity of the tcgen05 tensor-core convolution path (bf16): fprop, dgrad and wgrad through
+the module API on shapes the dispatcher sends to the tensor cores, against the CPU oracle
+evaluated in fp32 on the same bf16-rounded operands.  Tolerance: 2e-2 relative (BASELINE bf16)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import pose_oracle as po
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+CASES = [
+    # name            N  C     K    H   W   k  s  p  d  partial premasked bias
+    ("p3x3_64",       2, 64,   64,  32, 32, 3, 1, 1, 1, False, False, False),
+    ("p3x3_d2",       3, 128,  128, 16, 16, 3, 1, 2, 2, False, False, False),
+    ("p1x1_odd",      2, 256,  64,  9,  9,  1, 1, 0, 1, False, False, False),
+    ("p3x3_s2",       2, 128,  128, 17, 17, 3, 2, 1, 1, False, False, False),
+    ("p1x1_s2",       2, 256,  512, 16, 16, 1, 2, 0, 1, False, False, False),
+    ("p1x1_s2_odd",   2, 64,   128, 33, 33, 1, 2, 0, 1, False, False, False),
+    ("regressor",     2, 128,  272, 16, 16, 3, 1, 1, 1, False, False, True),
+    ("pc1x1",         2, 64,   256, 16, 16, 1, 1, 0, 1, True,  False, False),
+    ("pc3x3_pre",     2, 64,   64,  16, 16, 3, 1, 1, 1, True,  True,  False),
+    ("pc3x3_s2_pre",  2, 128,  128, 32, 32, 3, 2, 1, 1, True,  True,  False),
+    ("tiny_sp",       2, 512,  2048, 4, 4,  1, 1, 0, 1, False, False, False),
+    ("ragged65",      1, 64,   64,  65, 65, 3, 1, 1, 1, False, False, False),
+    ("deepK",         1, 2048, 512, 8,  8,  1, 1, 0, 1, False, False, False),
+    ("l4_3x3",        2, 512,  512, 16, 16, 3, 1, 2, 2, False, False, False),
+]
+
+
+def _uses_tc(b2pose, x_shape, K, k, s, p, d, flags):
+    L = b2pose._lib
+    desc = b2pose.ops.make_desc(x_shape, K, k, k, s, p, d, L.BF16, flags)
+    return [L.lib().b2_conv_uses_tensor_cores(C.byref(desc), op) for op in (0, 1, 2)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tc_conv(b2pose, dev, case):
+    name, N, Cin, K, H, W, k, s, p, d, partial, premasked, bias = case
+    L = b2pose._lib
+    gen = torch.Generator().manual_seed(abs(hash(name)) % (1 << 31))
+    bf = lambda t: t.bfloat16().float()
+    w = bf(torch.randn(K, Cin, k, k, generator=gen) * (2.0 / (k * k * K)) ** 0.5)
+    b = torch.randn(K, generator=gen) * 0.1 if bias else None
+    x = bf(torch.randn(N, Cin, H, W, generator=gen))
+    m = po.blob_mask(N, max(H, W), 0.35, gen)[:, :, :H, :W].contiguous() if partial else None
+    if premasked:
+        x = x * m
+    flags = (L.CONV_PARTIAL if partial else 0) | (L.CONV_X_PREMASKED if premasked else 0)
+    use = _uses_tc(b2pose, (N, H, W, Cin), K, k, s, p, d, flags)
+    assert use[0] == 1 and use[2] == 1, use            # these shapes must run on tcgen05
+
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if bias else None
+    if partial:
+        yr, mr = po.partial_conv(xr, m, wr, br, s, p, d)
+    else:
+        yr, mr = F.conv2d(xr, wr, br, s, p, d), None
+    cot = bf(torch.randn(yr.shape, generator=gen))
+    (yr * cot).sum().backward()
+
+    Conv = b2pose.PartialConv if partial else b2pose.Conv2d
+    conv = Conv(Cin, K, kernel_size=k, stride=s, padding=p, dilation=d, bias=bias).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_(w)
+        if bias:
+            conv.bias.copy_(b)
+    xg = x.permute(0, 2, 3, 1).contiguous().to(dev).bfloat16().requires_grad_(True)      # NHWC
+    if partial:
+        yg, mg = conv.forward_nhwc(xg, m[:, 0].contiguous().to(dev), premasked=premasked)
+        assert torch.equal(mg.cpu(), mr[:, 0])
+    else:
+        yg = conv.forward_nhwc(xg)
+    (yg.float() * cot.permute(0, 2, 3, 1).to(dev)).sum().backward()
+    errs = dict(y=rel_err(yg.permute(0, 3, 1, 2), yr), dw=rel_err(conv.weight.grad, wr.grad))
+    dx_ref = xr.grad * m if premasked else xr.grad     # premasked flow: the mask is applied upstream
+    dxg = xg.grad.permute(0, 3, 1, 2).float().cpu()
+    errs["dx"] = rel_err(dxg * m if premasked else dxg, dx_ref)
+    if bias:
+        errs["db"] = rel_err(conv.bias.grad, br.grad)
+    print(name, "tc(fprop,dgrad,wgrad)=", use, {k_: "%.2e" % v for k_, v in errs.items()})
+    bad = {k_: v for k_, v in errs.items() if not v < TOL}
+    assert not bad, (name, errs)
+
+
+def test_tc_matches_ffma_bits_of_mask_and_ratio(b2pose, dev):
+    """The tensor-core epilogue computes mask_out / ratio exactly like the CUDA-core kernel."""
+    L = b2pose._lib
+    gen = torch.Generator().manual_seed(4)
+    N, Cin, K, H, W = 2, 64, 64, 24, 24
+    x = torch.randn(N, H, W, Cin, generator=gen).to(dev).bfloat16()
+    m = po.blob_mask(N, H, 0.4, gen)[:, 0].contiguous().to(dev)
+    x = x * m.unsqueeze(-1).bfloat16()
+    w = (torch.randn(K, 3, 3, Cin, generator=gen) * 0.05).to(dev).bfloat16()
+    outs = []
+    for force in (0, L.CONV_FORCE_FFMA):
+        desc = b2pose.ops.make_desc((N, H, W, Cin), K, 3, 3, 1, 1, 1, L.BF16,
+                                    L.CONV_PARTIAL | L.CONV_X_PREMASKED | force)
+        y, mo, ratio, _ = b2pose.ops._conv_fprop(desc, x, m, w, None, True, False)
+        outs.append((y, mo, ratio))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert rel_err(outs[0][0], outs[1][0]) < 1e-2
