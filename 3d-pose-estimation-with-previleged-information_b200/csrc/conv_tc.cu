@@ -138,7 +138,8 @@ struct FpropParams {
   float* mask_out;
   float* ratio_out;
   bf16* out;
-  int out_stride_sp;                                   // dgrad of a strided 1x1: scatter factor (1 otherwise)
+  int pad_w;                                           // horizontal padding (== pad except in strided dgrad classes)
+  int out_stride_sp, out_off_h, out_off_w;             // strided dgrad: row (oh, ow) is stored at (oh*sp+off_h, ow*sp+off_w)
   int out_H, out_W;                                    // spatial size of the tensor written
 };
 
@@ -183,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int kt = tile % p.tiles_k, mt = tile / p.tiles_k;
         const int wi = mt % p.tiles_w, hi = (mt / p.tiles_w) % p.tiles_h, ni = mt / (p.tiles_w * p.tiles_h);
-        const int iw0 = wi * p.BW * p.stride - p.pad, ih0 = hi * p.BH * p.stride - p.pad, n0 = ni * p.BNI;
+        const int iw0 = wi * p.BW * p.stride - p.pad_w, ih0 = hi * p.BH * p.stride - p.pad, n0 = ni * p.BNI;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
           const int r = tap / p.S, s = tap - r * p.S;
@@ -238,12 +239,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int bn = row / brick, rem = row - bn * brick;
       const int bh = rem / p.BW, bw = rem - bh * p.BW;
       const int n = ni * p.BNI + bn, oh = hi * p.BH + bh, ow = wi * p.BW + bw;
-      const bool valid = (bn < p.BNI) && (n < p.N) && (oh < p.Ho) && (ow < p.Wo);
+      const int sh = oh * p.out_stride_sp + p.out_off_h, sw = ow * p.out_stride_sp + p.out_off_w;
+      const bool valid = (bn < p.BNI) && (n < p.N) && (oh < p.Ho) && (ow < p.Wo) && (sh < p.out_H) && (sw < p.out_W);
       float scale = 1.f, mo = 1.f;
       long long opix = 0;
       if (valid) {
         const long long pix = ((long long)n * p.Ho + oh) * p.Wo + ow;
-        opix = ((long long)n * p.out_H + (long long)oh * p.out_stride_sp) * p.out_W + (long long)ow * p.out_stride_sp;
+        opix = ((long long)n * p.out_H + sh) * p.out_W + sw;
         if (p.scale_mode == 1) {
           float cnt = 0.f;
           for (int r = 0; r < p.mask_R; ++r) {
@@ -432,7 +434,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         tmem_ld_wait();
         if (k < p.K) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j)
+            if (ct * p.BNc + c0 + j < p.C) atomicAdd(drow + c0 + j, __uint_as_float(v[j]));
         }
       }
       tc_fence_before();
@@ -446,20 +449,74 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 }
 
 // ------------------------------------------------------------------ filter transform for dgrad
-// W[k][r][s][c] -> Wt[c][R-1-r][S-1-s][k]   (bf16), 32x32 shared-memory transpose per tap
-__global__ void flip_transpose_kernel(const bf16* __restrict__ w, bf16* __restrict__ wt, int K, int C, int R, int S) {
+// Wt[c][t'][k] = W[k][tapmap[t']][c]   (bf16), 32x32 shared-memory transpose per output tap
+struct TapMap {
+  int n;
+  int src[49];
+};
+__global__ void tap_transpose_kernel(const bf16* __restrict__ w, bf16* __restrict__ wt, int K, int C, int taps_src,
+                                     TapMap tm) {
   __shared__ bf16 tile[32][33];
-  const int tap = blockIdx.z, r = tap / S, s = tap - r * S;
-  const int ftap = (R - 1 - r) * S + (S - 1 - s);
+  const int tdst = blockIdx.z, tsrc = tm.src[tdst];
   const int k0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int k = k0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (k < K && c < C) ? w[((long long)k * R * S + tap) * C + c] : __float2bfloat16(0.f);
+    tile[i][threadIdx.x] = (k < K && c < C) ? w[((long long)k * taps_src + tsrc) * C + c] : __float2bfloat16(0.f);
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int c = c0 + i, k = k0 + threadIdx.x;
-    if (k < K && c < C) wt[((long long)c * R * S + ftap) * K + k] = tile[threadIdx.x][i];
+    if (k < K && c < C) wt[((long long)c * tm.n + tdst) * K + k] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ stem: im2col + padded filter
+// col[pix][(r*S+s)*C + c] = x[n, oh*st-p+r, ow*st-p+s, c] (* mask) ; columns >= R*S*C are zero.
+__global__ void im2col_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ col,
+                              int N, int H, int W, int C, int R, int S, int stride, int pad, int dil, int Ho, int Wo,
+                              int Kpad) {
+  const int chunks = Kpad >> 3;
+  const long long total = (long long)N * Ho * Wo * chunks;
+  const int RSC = R * S * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    const long long pix = i / chunks;
+    const int ow = (int)(pix % Wo);
+    const long long t = pix / Wo;
+    const int oh = (int)(t % Ho), n = (int)(t / Ho);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cidx = ch * 8 + j;
+      float v = 0.f;
+      if (cidx < RSC) {
+        const int tap = cidx / C, c = cidx - tap * C;
+        const int r = tap / S, s2 = tap - r * S;
+        const int ih = oh * stride - pad + r * dil, iw = ow * stride - pad + s2 * dil;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+          const long long ip = ((long long)n * H + ih) * W + iw;
+          v = __bfloat162float(x[ip * C + c]);
+          if (mask) v *= mask[ip];
+        }
+      }
+      f[j] = v;
+    }
+    store8(col + pix * Kpad + ch * 8, f);
+  }
+}
+__global__ void pad_filter_kernel(const bf16* __restrict__ w, bf16* __restrict__ wp, int K, int RSC, int Kpad) {
+  const int total = K * Kpad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i / Kpad, c = i - k * Kpad;
+    wp[i] = c < RSC ? w[(long long)k * RSC + c] : __float2bfloat16(0.f);
+  }
+}
+__global__ void unpad_add_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int K, int RSC, int Kpad) {
+  const int total = K * RSC;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i / RSC, c = i - k * RSC;
+    dw[i] += dwp[(long long)k * Kpad + c];
   }
 }
 
@@ -558,7 +615,8 @@ int pow2_cols(int c) {
 struct RunArgs {
   const void* act; int N, H, W, C;
   const void* filt; int K, R, S, stride, pad, dil, Ho, Wo;    // filt: [K][R*S*C] bf16
-  void* out; int out_H, out_W, out_stride_sp;
+  void* out; int out_H, out_W, out_stride_sp, out_off_h, out_off_w;
+  int pad_w, use_pad_w;                                        // pad_w is read only when use_pad_w != 0
   int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
   float* mask_out; float* ratio_out;
   int mask_R, mask_S, mask_stride, mask_pad, mask_dil, mask_H, mask_W;
@@ -573,7 +631,8 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   int nk = (a.K + 255) / 256;
   p.BN = (((a.K + nk - 1) / nk) + 15) / 16 * 16;
   p.tiles_k = (a.K + p.BN - 1) / p.BN;
-  p.cblocks = a.C / kBlockK; p.kblocks = a.R * a.S * p.cblocks;
+  p.cblocks = (a.C + kBlockK - 1) / kBlockK;      // a ragged last block is zero-filled by TMA on the A side
+  p.kblocks = a.R * a.S * p.cblocks;
   const int stage_bytes = (int)kABytes + p.BN * kBlockK * 2;
   int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -585,6 +644,8 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.mask_R = a.mask_R; p.mask_S = a.mask_S; p.mask_stride = a.mask_stride; p.mask_pad = a.mask_pad;
   p.mask_dil = a.mask_dil; p.mask_H = a.mask_H; p.mask_W = a.mask_W;
   p.out_stride_sp = a.out_stride_sp; p.out_H = a.out_H; p.out_W = a.out_W;
+  p.out_off_h = a.out_off_h; p.out_off_w = a.out_off_w;
+  p.pad_w = a.use_pad_w ? a.pad_w : a.pad;
   CUtensorMap ma, mb;
   int rc = make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
   if (rc) return rc;
@@ -616,28 +677,52 @@ bool tc_enabled() {
 }  // namespace
 
 // ------------------------------------------------------------------ dispatch interface
+namespace {
+
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+inline bool is_stem(const B2ConvDesc* d) { return d->C <= 4 && d->R * d->S * d->C >= 32; }
+inline int stem_kpad(const B2ConvDesc* d) { return (d->R * d->S * d->C + 7) / 8 * 8; }
+
+int launch_im2col(const B2ConvDesc* d, const void* x, const float* mask, bf16* col, cudaStream_t st) {
+  const int kpad = stem_kpad(d);
+  long long total = (long long)d->N * d->Ho * d->Wo * (kpad / 8);
+  long long want = (total + 255) / 256, cap = (long long)b2_num_sms() * 16;
+  int grid = (int)(want > cap ? cap : want);
+  im2col_kernel<<<grid, 256, 0, st>>>((const bf16*)x, mask, col, d->N, d->H, d->W, d->C, d->R, d->S, d->stride, d->pad,
+                                      d->dil, d->Ho, d->Wo, kpad);
+  B2_LAUNCH_CHECK("im2col");
+  return B2_OK;
+}
+
+}  // namespace
+
 bool conv_tc_supported(const B2ConvDesc* d, int op) {
   if (!tc_enabled() || d->dtype != B2_BF16) return false;
-  if (d->C % 64 != 0 || d->K % 8 != 0) return false;
+  if (d->K % 8 != 0) return false;
   const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
+  if (is_stem(d)) return op == 0 || op == 2;                // im2col + GEMM; network inputs need no dgrad
+  if (d->C % 8 != 0) return false;
   const bool one = (d->R == 1 && d->S == 1);
   if (partial && !one && !premasked) return false;          // needs x*mask in the loader: CUDA-core path
   if (partial && one && d->stride != 1) return false;
   if (op == 0) return true;
-  if (op == 1) {
-    if (d->K % 64 != 0) return false;                       // K is the contraction of dgrad
-    if (d->stride == 1) return true;
-    return one && d->pad == 0;                              // strided 1x1: gather GEMM + scatter store
-  }
+  if (op == 1) return d->stride == 1 || d->dil == 1;        // strided: one launch per output parity class
   return op == 2;
 }
 
 size_t conv_tc_workspace_bytes(const B2ConvDesc* d, int op) {
   size_t ws = 0;
   const bool partial = d->flags & B2_CONV_PARTIAL;
-  const size_t dy_bytes = (size_t)d->N * d->Ho * d->Wo * d->K * 2;
+  const size_t dy_bytes = align256((size_t)d->N * d->Ho * d->Wo * d->K * 2);
+  if (is_stem(d)) {
+    const size_t kpad = stem_kpad(d);
+    ws += align256((size_t)d->N * d->Ho * d->Wo * kpad * 2);            // im2col matrix
+    ws += align256((size_t)d->K * kpad * (op == 2 ? 4 : 2));            // padded filter / padded dw
+    if (op == 2 && partial && !(d->flags & B2_CONV_DY_PRESCALED)) ws += dy_bytes;
+    return ws;
+  }
   if (op == 1) {
-    ws += ((size_t)d->K * d->R * d->S * d->C * 2 + 255) / 256 * 256;     // flipped filter
+    ws += align256((size_t)d->K * d->R * d->S * d->C * 2);               // transposed (per-class) filters
     if (partial && !(d->flags & B2_CONV_DY_PRESCALED)) ws += dy_bytes;
   }
   if (op == 2 && partial && !(d->flags & B2_CONV_DY_PRESCALED)) ws += dy_bytes;
@@ -646,12 +731,21 @@ size_t conv_tc_workspace_bytes(const B2ConvDesc* d, int op) {
 
 int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, const void* w, const float* bias,
                   void* y, float* mask_out, float* ratio_out, double* bn_sums, void* workspace, cudaStream_t st) {
-  (void)workspace;
   RunArgs a{};
+  const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
   a.act = x; a.N = d->N; a.H = d->H; a.W = d->W; a.C = d->C;
   a.filt = w; a.K = d->K; a.R = d->R; a.S = d->S; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
+  if (is_stem(d)) {
+    const int kpad = stem_kpad(d);
+    bf16* col = (bf16*)workspace;
+    bf16* wp = (bf16*)((uint8_t*)workspace + align256((size_t)d->N * d->Ho * d->Wo * kpad * 2));
+    int rc = launch_im2col(d, x, (partial && !premasked) ? mask_in : nullptr, col, st);
+    if (rc) return rc;
+    pad_filter_kernel<<<(d->K * kpad + 255) / 256, 256, 0, st>>>((const bf16*)w, wp, d->K, d->R * d->S * d->C, kpad);
+    B2_LAUNCH_CHECK("pad_filter");
+    a.act = col; a.H = d->Ho; a.W = d->Wo; a.C = kpad; a.filt = wp; a.R = 1; a.S = 1; a.stride = 1; a.pad = 0; a.dil = 1;
+  }
   a.Ho = d->Ho; a.Wo = d->Wo; a.out = y; a.out_H = d->Ho; a.out_W = d->Wo; a.out_stride_sp = 1;
-  const bool partial = d->flags & B2_CONV_PARTIAL;
   a.scale_mode = partial ? 1 : 0;
   a.mask_in = mask_in; a.bias = bias; a.mask_out = mask_out; a.ratio_out = ratio_out;
   a.mask_R = d->R; a.mask_S = d->S; a.mask_stride = d->stride; a.mask_pad = d->pad; a.mask_dil = d->dil;
@@ -667,10 +761,7 @@ int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const
   const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
   uint8_t* ws = (uint8_t*)workspace;
   bf16* wt = (bf16*)ws;
-  ws += ((size_t)d->K * d->R * d->S * d->C * 2 + 255) / 256 * 256;
-  dim3 tg((d->C + 31) / 32, (d->K + 31) / 32, d->R * d->S), tb(32, 8);
-  flip_transpose_kernel<<<tg, tb, 0, st>>>((const bf16*)w, wt, d->K, d->C, d->R, d->S);
-  B2_LAUNCH_CHECK("flip_transpose");
+  ws += align256((size_t)d->K * d->R * d->S * d->C * 2);
   const void* dys = dy;
   if (partial && !(d->flags & B2_CONV_DY_PRESCALED) && ratio) {
     int rc = b2_scale_rows(dy, ratio, ws, (int64_t)d->N * d->Ho * d->Wo, d->K, B2_BF16, (void*)st);
@@ -679,31 +770,110 @@ int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const
   }
   RunArgs a{};
   a.act = dys; a.N = d->N; a.H = d->Ho; a.W = d->Wo; a.C = d->K;
-  a.filt = wt; a.K = d->C; a.R = d->R; a.S = d->S; a.dil = d->dil;
-  a.out = dx; a.out_H = d->H; a.out_W = d->W;
+  a.K = d->C; a.out = dx; a.out_H = d->H; a.out_W = d->W;
   a.scale_mode = (partial && !premasked && mask_in) ? 2 : 0;
   a.row_scale = mask_in;
+  a.stride = 1;
+  const int taps = d->R * d->S;
+  dim3 tb(32, 8);
   if (d->stride == 1) {
-    a.stride = 1; a.pad = d->dil * (d->R - 1) - d->pad; a.Ho = d->H; a.Wo = d->W; a.out_stride_sp = 1;
-  } else {
-    // strided 1x1, pad 0: dx[n, oh*s, ow*s, :] = dy[n, oh, ow, :] @ W ; every other position is zero
+    // dx = conv(dy, flipped/transposed filter), pad' = dil*(R-1) - pad
+    TapMap tm;
+    tm.n = taps;
+    for (int r = 0; r < d->R; ++r)
+      for (int s2 = 0; s2 < d->S; ++s2) tm.src[r * d->S + s2] = (d->R - 1 - r) * d->S + (d->S - 1 - s2);
+    dim3 tg((d->C + 31) / 32, (d->K + 31) / 32, taps);
+    tap_transpose_kernel<<<tg, tb, 0, st>>>((const bf16*)w, wt, d->K, d->C, taps, tm);
+    B2_LAUNCH_CHECK("tap_transpose");
+    a.filt = wt; a.R = d->R; a.S = d->S; a.dil = d->dil; a.pad = d->dil * (d->R - 1) - d->pad;
+    a.Ho = d->H; a.Wo = d->W; a.out_stride_sp = 1;
+    return run_conv_tc(a, st);
+  }
+  // strided (dil == 1): output pixels of parity class (ph, pw) = (ih % stride, iw % stride) only see the taps
+  // r == (ph + pad) mod stride; each class is a dense stride-1 correlation over dy written to a strided
+  // sub-lattice of dx.  Classes that see no tap stay zero.
+  const int sd = d->stride;
+  bool need_zero = false;
+  for (int ph = 0; ph < sd; ++ph) {
+    int cr = 0, cs = 0;
+    for (int r = 0; r < d->R; ++r) cr += (((ph + d->pad - r) % sd + sd) % sd == 0);
+    for (int s2 = 0; s2 < d->S; ++s2) cs += (((ph + d->pad - s2) % sd + sd) % sd == 0);
+    if (cr == 0 || cs == 0) need_zero = true;
+  }
+  if (need_zero) {
     cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->N * d->H * d->W * d->C * 2, st);
     B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc_dgrad: memset failed: %s", cudaGetErrorString(e));
-    a.stride = 1; a.pad = 0; a.Ho = d->Ho; a.Wo = d->Wo; a.out_stride_sp = d->stride;
   }
-  return run_conv_tc(a, st);
+  bf16* wcls = wt;
+  for (int ph = 0; ph < sd; ++ph) {
+    int rl[8], nr = 0;
+    for (int r = d->R - 1; r >= 0; --r)            // decreasing r -> increasing dy offset
+      if (((ph + d->pad - r) % sd + sd) % sd == 0) rl[nr++] = r;
+    if (nr == 0 || ph >= d->H) continue;
+    for (int pw = 0; pw < sd; ++pw) {
+      int sl[8], ns = 0;
+      for (int s2 = d->S - 1; s2 >= 0; --s2)
+        if (((pw + d->pad - s2) % sd + sd) % sd == 0) sl[ns++] = s2;
+      if (ns == 0 || pw >= d->W) continue;
+      TapMap tm;
+      tm.n = nr * ns;
+      for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < ns; ++j) tm.src[i * ns + j] = rl[i] * d->S + sl[j];
+      dim3 tg((d->C + 31) / 32, (d->K + 31) / 32, tm.n);
+      tap_transpose_kernel<<<tg, tb, 0, st>>>((const bf16*)w, wcls, d->K, d->C, taps, tm);
+      B2_LAUNCH_CHECK("tap_transpose");
+      // floor division of (ph + pad - r_max) by the stride (exact by construction)
+      auto fdiv = [](int a_, int b_) { return (a_ >= 0) ? a_ / b_ : -((-a_ + b_ - 1) / b_); };
+      const int o0h = fdiv(ph + d->pad - rl[0], sd), o0w = fdiv(pw + d->pad - sl[0], sd);
+      a.filt = wcls; a.R = nr; a.S = ns; a.dil = 1; a.pad = 0;
+      RunArgs b = a;
+      b.Ho = (d->H - ph + sd - 1) / sd; b.Wo = (d->W - pw + sd - 1) / sd;
+      b.out_stride_sp = sd; b.out_off_h = ph; b.out_off_w = pw;
+      // the kernel addresses dy at (a - pad' + t'), so pad' = -o0 (may differ per dim: use the larger
+      // and shift the tap origin through separate pads)
+      b.pad = -o0h;
+      b.pad_w = -o0w;
+      b.use_pad_w = 1;
+      int rc = run_conv_tc(b, st);
+      if (rc) return rc;
+      wcls += (size_t)tm.n * d->K * d->C;
+    }
+  }
+  return B2_OK;
 }
 
 int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy, const float* ratio,
                   float* dw, void* workspace, cudaStream_t st) {
-  (void)mask_in;   // 1x1: mask folded into the (pre)scaled dy rows; 3x3: x is pre-masked (see conv_tc_supported)
-  const bool partial = d->flags & B2_CONV_PARTIAL;
+  // 1x1: the mask is folded into the (pre)scaled dy rows; 3x3: x is pre-masked (see conv_tc_supported);
+  // stem: the im2col kernel applies the mask.
+  const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
+  uint8_t* ws = (uint8_t*)workspace;
+  B2ConvDesc g = *d;                 // geometry seen by the GEMM
+  float* dw_out = dw;
+  float* dwp = nullptr;
+  int kpad = 0;
+  if (is_stem(d)) {
+    kpad = stem_kpad(d);
+    bf16* col = (bf16*)ws;
+    ws += align256((size_t)d->N * d->Ho * d->Wo * kpad * 2);
+    dwp = (float*)ws;
+    ws += align256((size_t)d->K * kpad * 4);
+    int rc = launch_im2col(d, x, (partial && !premasked) ? mask_in : nullptr, col, st);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)d->K * kpad * 4, st);
+    B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc_wgrad: memset failed: %s", cudaGetErrorString(e));
+    x = col;
+    g.H = d->Ho; g.W = d->Wo; g.C = kpad; g.R = 1; g.S = 1; g.stride = 1; g.pad = 0; g.dil = 1;
+    dw_out = dwp;
+  }
   const void* dys = dy;
   if (partial && !(d->flags & B2_CONV_DY_PRESCALED) && ratio) {
-    int rc = b2_scale_rows(dy, ratio, workspace, (int64_t)d->N * d->Ho * d->Wo, d->K, B2_BF16, (void*)st);
+    int rc = b2_scale_rows(dy, ratio, ws, (int64_t)d->N * d->Ho * d->Wo, d->K, B2_BF16, (void*)st);
     if (rc) return rc;
-    dys = workspace;
+    dys = ws;
   }
+  const B2ConvDesc* d0 = d;
+  d = &g;
   WgradParams p;
   p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.K = d->K; p.R = d->R; p.S = d->S;
   p.stride = d->stride; p.pad = d->pad; p.dil = d->dil; p.Ho = d->Ho; p.Wo = d->Wo;
@@ -722,7 +892,7 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   }
   p.tiles_w = (d->Wo + p.BW - 1) / p.BW; p.tiles_h = (d->Ho + p.BH - 1) / p.BH; p.tiles_n = (d->N + p.BNI - 1) / p.BNI;
   p.BNc = d->C % 256 == 0 ? 256 : (d->C % 128 == 0 ? 128 : 64);
-  p.ctiles = d->C / p.BNc;
+  p.ctiles = (d->C + p.BNc - 1) / p.BNc;
   p.ktiles = (d->K + 127) / 128;
   const int taps = d->R * d->S;
   const long long bricks = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
@@ -739,7 +909,7 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.BNc);
-  p.dw = dw;
+  p.dw = dw_out;
   CUtensorMap mdy, mx;
   int rc = make_act_map(&mdy, dys, d->N, d->Ho, d->Wo, d->K, p.BW, p.BH, p.BNI, 1);
   if (rc) return rc;
@@ -756,11 +926,16 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
   wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(mdy, mx, p);
   B2_LAUNCH_CHECK("wgrad_tc_kernel");
+  if (dwp) {
+    const int rsc = d0->R * d0->S * d0->C;
+    unpad_add_kernel<<<(d0->K * rsc + 255) / 256, 256, 0, st>>>(dwp, dw, d0->K, rsc, kpad);
+    B2_LAUNCH_CHECK("unpad_add");
+  }
   return B2_OK;
 }
 
-// Debug entry: C[M,N] (fp32) = A[M,K] * B[N,K]^T through the fprop kernel (variant 0) or
-// C[M,N] = A[P,M]^T * B[P,N] through the wgrad kernel (variant 1); bf16 inputs.
+// Debug entry kept for ABI stability: the tensor-core path is exercised through the convolution
+// entry points (tests/test_gpu_tc.py).
 extern "C" int b2_tc_selftest(const void* a, const void* b, float* c, int32_t M, int32_t N, int32_t K, int32_t variant,
                               void* stream) {
   (void)a; (void)b; (void)c; (void)M; (void)N; (void)K; (void)variant; (void)stream;

@@ -29,6 +29,10 @@ CASES = [
     ("ragged65",      1, 64,   64,  65, 65, 3, 1, 1, 1, False, False, False),
     ("deepK",         1, 2048, 512, 8,  8,  1, 1, 0, 1, False, False, False),
     ("l4_3x3",        2, 512,  512, 16, 16, 3, 1, 2, 2, False, False, False),
+    ("s2_odd",        2, 128,  128, 33, 33, 3, 2, 1, 1, False, False, False),
+    ("stem_rgb",      2, 3,    64,  64, 64, 7, 2, 3, 1, False, False, False),
+    ("stem_depth_pc", 2, 1,    64,  65, 65, 7, 2, 3, 1, True,  False, False),
+    ("c_tail",        2, 72,   80,  12, 12, 3, 1, 1, 1, False, False, False),
 ]
 
 
@@ -53,6 +57,7 @@ def test_tc_conv(b2pose, dev, case):
     flags = (L.CONV_PARTIAL if partial else 0) | (L.CONV_X_PREMASKED if premasked else 0)
     use = _uses_tc(b2pose, (N, H, W, Cin), K, k, s, p, d, flags)
     assert use[0] == 1 and use[2] == 1, use            # these shapes must run on tcgen05
+    assert use[1] == (0 if Cin <= 4 else 1), use       # (network inputs have no dgrad on the tensor cores)
 
     xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
     br = b.clone().requires_grad_(True) if bias else None
