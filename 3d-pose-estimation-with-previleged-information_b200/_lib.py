@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libb2pose.so")
 
 F32, BF16 = 0, 1
 CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA = 1, 2, 4, 8
-ABI_VERSION = 1
+ABI_VERSION = 2
+BN_PARTS = 320
 
 
 class ConvDesc(C.Structure):
@@ -41,9 +42,11 @@ SIGNATURES = {
     "b2_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
     "b2_cast_f32_to_bf16": [_p, _p, _l, _p],
     "b2_bn_stats": [_p, _l, _i, _i, _p, _p],
-    "b2_bn_apply": [_p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _i, _p, _p, _p, _l, _i, _i, _p],
-    "b2_bn_bwd_reduce": [_p, _p, _p, _p, _p, _p, _i, _p, _l, _i, _i, _p],
-    "b2_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p],
+    "b2_bn_finalize": [_p, _l, _i, _p, _p, _f, _f, _i, _p, _p, _p],
+    "b2_bn_apply": [_p, _p, _p, _p, _p, _p, _p, _i, _p, _l, _i, _i, _p],
+    "b2_bn_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _l, _i, _i, _p],
+    "b2_bn_bwd_finalize": [_p, _i, _p, _p, _p, _p],
+    "b2_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _l, _i, _i, _p],
     "b2_maxpool3x3s2_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2_maxpool3x3s2_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2_head_fwd": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],

@@ -49,7 +49,7 @@ extern "C" size_t b2_conv_workspace_bytes(const B2ConvDesc* d, int op) {
 }
 
 extern "C" int b2_pconv_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, const void* w,
-                              const float* bias, void* y, float* mask_out, float* ratio_out, double* bn_sums,
+                              const float* bias, void* y, float* mask_out, float* ratio_out, float* bn_sums,
                               void* workspace, size_t ws_bytes, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;

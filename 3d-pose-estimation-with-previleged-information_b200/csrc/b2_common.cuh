@@ -113,7 +113,7 @@ int conv_ffma_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, co
 bool conv_tc_supported(const B2ConvDesc* d, int op);
 size_t conv_tc_workspace_bytes(const B2ConvDesc* d, int op);
 int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, const void* w, const float* bias,
-                  void* y, float* mask_out, float* ratio_out, double* bn_sums, void* workspace, cudaStream_t st);
+                  void* y, float* mask_out, float* ratio_out, float* bn_sums, void* workspace, cudaStream_t st);
 int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w, const float* mask_in,
                   void* dx, void* workspace, cudaStream_t st);
 int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy, const float* ratio,

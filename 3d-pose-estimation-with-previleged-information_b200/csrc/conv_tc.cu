@@ -29,6 +29,7 @@ constexpr int kMaxStages = 8;
 constexpr int kTileM = 128;          // UMMA M (output pixels per tile / TMEM lanes)
 constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
 constexpr uint32_t kABytes = kTileM * kBlockK * 2;
+constexpr int kStaging = 4;          // 16 KB output staging buffers of the TMA-store epilogue
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,6 +79,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -141,6 +152,8 @@ struct FpropParams {
   int pad_w;                                           // horizontal padding (== pad except in strided dgrad classes)
   int out_stride_sp, out_off_h, out_off_w;             // strided dgrad: row (oh, ow) is stored at (oh*sp+off_h, ow*sp+off_w)
   int out_H, out_W;                                    // spatial size of the tensor written
+  int tma_store;                                       // epilogue: smem-staged TMA store (+ fused BN statistics)
+  float* bn_sums;                                      // partials[B2_BN_PARTS][2*K]: sum / sum of squares of the stored output
 };
 
 struct __align__(8) PipeBars {
@@ -150,13 +163,18 @@ struct __align__(8) PipeBars {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const FpropParams p) {
+               const __grid_constant__ CUtensorMap map_out, const FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
   const uint32_t stage_bytes = kABytes + b_bytes;
-  PipeBars* bars = reinterpret_cast<PipeBars*>(smem + (size_t)p.stages * stage_bytes);
+  // layout: [stages][A|B] | kStaging x 16 KB output staging (TMA-store epilogue) | barriers | fp32 statistics [2*K]
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
+  PipeBars* bars = reinterpret_cast<PipeBars*>(staging + (p.tma_store ? kStaging * kABytes : 0));
+  float* s_stats = reinterpret_cast<float*>(bars + 1);
+  if (p.bn_sums)      // [4 epilogue warps][2*K]: warp-private partials, no shared atomics
+    for (int i = threadIdx.x; i < 8 * p.K; i += kThreads) s_stats[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
@@ -168,6 +186,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     fence_barrier_init();
     prefetch_map(&map_a);
     prefetch_map(&map_b);
+    if (p.tma_store) prefetch_map(&map_out);
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -231,6 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row = q * 32 + lane;
     const int brick = p.BW * p.BH;
     int local = 0;
+    int ep_group = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -271,6 +291,80 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
       const int kbase = kt * p.BN;
+      if (p.tma_store) {
+        // ---- smem-staged epilogue: 64-column groups -> swizzled staging tile -> TMA store; the
+        //      staged (rounded) values also feed the per-channel BatchNorm statistics.
+        const int ep_tid = threadIdx.x - 64;
+        const int groups = p.BN >> 6;
+        for (int g = 0; g < groups; ++g) {
+          uint8_t* sbuf = staging + (size_t)(ep_group & (kStaging - 1)) * kABytes;
+          ++ep_group;
+          if (ep_tid == 0) bulk_wait_read<kStaging - 1>();   // the store issued kStaging groups ago has drained this buffer
+          epi_barrier();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld16(taddr + g * 64 + h * 32, v);
+            tmem_ld16(taddr + g * 64 + h * 32 + 16, v + 16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = valid ? __uint_as_float(v[j * 8 + e]) * scale : 0.f;
+              const int chunk = h * 4 + j;
+              store8(reinterpret_cast<bf16*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)), f);
+            }
+          }
+          if (g == groups - 1) {                          // accumulator fully read: hand TMEM back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+          }
+          fence_async_smem();
+          epi_barrier();
+          if (ep_tid == 0) {
+            tma_store_4d(&map_out, smem_u32(sbuf), kbase + g * 64, wi * p.BW, hi * p.BH, ni * p.BNI);
+            bulk_commit();
+          }
+          if (p.bn_sums) {
+            // per-channel sum / sum of squares of the staged (bf16-rounded) tile: 16-byte shared loads
+            // (a quarter-warp reads one whole 128-byte row), two shuffle steps, 8 lanes x 16 shared atomics
+            const int chunk = ep_tid & 7, rsub = ep_tid >> 3;
+            const int nrows = min(brick * p.BNI, kTileM);
+            float su[8], sq[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) su[e] = sq[e] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = rsub + 16 * i;
+              if (r < nrows) {
+                float t[8];
+                load8(reinterpret_cast<const bf16*>(sbuf + r * 128 + ((chunk ^ (r & 7)) << 4)), t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { su[e] += t[e]; sq[e] = fmaf(t[e], t[e], sq[e]); }
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              su[e] += __shfl_xor_sync(0xffffffffu, su[e], 8);
+              sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 8);
+              su[e] += __shfl_xor_sync(0xffffffffu, su[e], 16);
+              sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
+            }
+            const int ch0 = kbase + g * 64 + chunk * 8;
+            if (lane < 8 && ch0 < p.K) {
+              float* mine = s_stats + (size_t)q * 2 * p.K;       // q = this warp's quarter
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                mine[ch0 + e] += su[e];
+                mine[p.K + ch0 + e] += sq[e];
+              }
+            }
+          }
+        }
+        continue;
+      }
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
         const bool two = (c0 + 16) < p.BN;
@@ -300,10 +394,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tempty[acc]);
     }
+    if (p.tma_store && threadIdx.x == 64) bulk_wait_read<0>();     // staging must outlive the last store
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (p.bn_sums) {      // this CTA's slot of partials[B2_BN_PARTS][2K]; the unused slots are zero-filled
+    float* slot = p.bn_sums + (size_t)blockIdx.x * 2 * p.K;
+    for (int i = threadIdx.x; i < 2 * p.K; i += kThreads)
+      slot[i] = (s_stats[i] + s_stats[2 * p.K + i]) + (s_stats[4 * p.K + i] + s_stats[6 * p.K + i]);
+    for (int sl = gridDim.x + blockIdx.x; sl < B2_BN_PARTS; sl += gridDim.x)
+      for (int i = threadIdx.x; i < 2 * p.K; i += kThreads) p.bn_sums[(size_t)sl * 2 * p.K + i] = 0.f;
+  }
 }
 
 // ------------------------------------------------------------------ wgrad kernel
@@ -434,8 +536,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         tmem_ld_wait();
         if (k < p.K) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ct * p.BNc + c0 + j < p.C) atomicAdd(drow + c0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)          // 16-byte vector reductions (C % 8 == 0 keeps groups whole)
+            if (ct * p.BNc + c0 + j < p.C)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + j),
+                           "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                           "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
         }
       }
       tc_fence_before();
@@ -471,38 +577,46 @@ __global__ void tap_transpose_kernel(const bf16* __restrict__ w, bf16* __restric
 }
 
 // ------------------------------------------------------------------ stem: im2col + padded filter
-// col[pix][(r*S+s)*C + c] = x[n, oh*st-p+r, ow*st-p+s, c] (* mask) ; columns >= R*S*C are zero.
-__global__ void im2col_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ col,
-                              int N, int H, int W, int C, int R, int S, int stride, int pad, int dil, int Ho, int Wo,
-                              int Kpad) {
-  const int chunks = Kpad >> 3;
-  const long long total = (long long)N * Ho * Wo * chunks;
-  const int RSC = R * S * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % chunks);
-    const long long pix = i / chunks;
-    const int ow = (int)(pix % Wo);
-    const long long t = pix / Wo;
-    const int oh = (int)(t % Ho), n = (int)(t / Ho);
+// col[pix][(r*S+s)*C + c] = x[n, oh*st-p+r*dil, ow*st-p+s*dil, c] (* mask) ; columns >= R*S*C are zero.
+// One CTA per output row: the R input rows it needs are staged in shared memory (coalesced reads,
+// zero borders, mask applied), then every thread assembles 16-byte column chunks from shared memory
+// and writes them coalesced.
+__global__ void __launch_bounds__(256)
+im2col_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ col, int N, int H, int W,
+              int C, int R, int S, int stride, int pad, int dil, int Ho, int Wo, int Kpad) {
+  extern __shared__ float rows_sm[];            // [R][Wp*C], Wp = W + 2*pad
+  const int Wp = W + 2 * pad, rowlen = Wp * C;
+  const int oh = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  for (int i = threadIdx.x; i < R * rowlen; i += blockDim.x) {
+    const int r = i / rowlen, j = i - r * rowlen;
+    const int iw = j / C - pad, c = j - (j / C) * C;
+    const int ih = oh * stride - pad + r * dil;
+    float v = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      const long long ip = ((long long)n * H + ih) * W + iw;
+      v = __bfloat162float(x[ip * C + c]);
+      if (mask) v *= mask[ip];
+    }
+    rows_sm[i] = v;
+  }
+  __syncthreads();
+  const int chunks = Kpad >> 3, RSC = R * S * C, SC = S * C;
+  const long long pix0 = ((long long)n * Ho + oh) * Wo;
+  for (int i = threadIdx.x; i < Wo * chunks; i += blockDim.x) {
+    const int ow = i / chunks, ch = i - ow * chunks;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int cidx = ch * 8 + j;
       float v = 0.f;
       if (cidx < RSC) {
-        const int tap = cidx / C, c = cidx - tap * C;
-        const int r = tap / S, s2 = tap - r * S;
-        const int ih = oh * stride - pad + r * dil, iw = ow * stride - pad + s2 * dil;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-          const long long ip = ((long long)n * H + ih) * W + iw;
-          v = __bfloat162float(x[ip * C + c]);
-          if (mask) v *= mask[ip];
-        }
+        const int r = cidx / SC, rem = cidx - r * SC;       // rem = s*C + c
+        const int s2 = rem / C, c = rem - s2 * C;
+        v = rows_sm[r * rowlen + (ow * stride + s2 * dil) * C + c];
       }
       f[j] = v;
     }
-    store8(col + pix * Kpad + ch * 8, f);
+    store8(col + (pix0 + ow) * Kpad + ch * 8, f);
   }
 }
 __global__ void pad_filter_kernel(const bf16* __restrict__ w, bf16* __restrict__ wp, int K, int RSC, int Kpad) {
@@ -617,6 +731,7 @@ struct RunArgs {
   const void* filt; int K, R, S, stride, pad, dil, Ho, Wo;    // filt: [K][R*S*C] bf16
   void* out; int out_H, out_W, out_stride_sp, out_off_h, out_off_w;
   int pad_w, use_pad_w;                                        // pad_w is read only when use_pad_w != 0
+  float* bn_sums; bool* stats_fused;                          // optional fused BatchNorm statistics
   int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
   float* mask_out; float* ratio_out;
   int mask_R, mask_S, mask_stride, mask_pad, mask_dil, mask_H, mask_W;
@@ -634,7 +749,14 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.cblocks = (a.C + kBlockK - 1) / kBlockK;      // a ragged last block is zero-filled by TMA on the A side
   p.kblocks = a.R * a.S * p.cblocks;
   const int stage_bytes = (int)kABytes + p.BN * kBlockK * 2;
-  int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars)) / stage_bytes;
+  static const bool no_tma_store = getenv("B2POSE_TC_NO_TMA_STORE") != nullptr;      // tuning switches
+  static const bool no_fused_stats = getenv("B2POSE_TC_NO_FUSED_STATS") != nullptr;
+  p.tma_store = (p.BN % 64 == 0 && a.out_stride_sp == 1 && !no_tma_store) ? 1 : 0;
+  // fused statistics for the wide-spatial layers (K <= 512); deep layers are small and keep the separate pass
+  p.bn_sums = (p.tma_store && a.bn_sums && a.K <= 512 && !no_fused_stats) ? a.bn_sums : nullptr;
+  if (a.stats_fused) *a.stats_fused = p.bn_sums != nullptr;
+  const int extra = (p.tma_store ? kStaging * (int)kABytes : 0) + (p.bn_sums ? 32 * a.K : 0);
+  int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars) - extra) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   B2_REQUIRE(stages >= 2, B2_E_UNSUPPORTED, "conv_tc: not enough shared memory for two stages");
   p.stages = stages;
@@ -646,12 +768,18 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.out_stride_sp = a.out_stride_sp; p.out_H = a.out_H; p.out_W = a.out_W;
   p.out_off_h = a.out_off_h; p.out_off_w = a.out_off_w;
   p.pad_w = a.use_pad_w ? a.pad_w : a.pad;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo;
   int rc = make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
   if (rc) return rc;
   rc = make_mat_map(&mb, a.filt, a.K, (long long)a.R * a.S * a.C, p.BN);
   if (rc) return rc;
-  const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024;
+  if (p.tma_store) {
+    rc = make_act_map(&mo, a.out, a.N, a.out_H, a.out_W, a.K, p.BW, p.BH, p.BNI, 1);
+    if (rc) return rc;
+  } else {
+    mo = ma;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024 + extra;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit());
@@ -660,7 +788,7 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   }
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_k;
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
-  conv_tc_kernel<<<grid, kThreads, smem, st>>>(ma, mb, p);
+  conv_tc_kernel<<<grid, kThreads, smem, st>>>(ma, mb, mo, p);
   B2_LAUNCH_CHECK("conv_tc_kernel");
   return B2_OK;
 }
@@ -685,11 +813,11 @@ inline int stem_kpad(const B2ConvDesc* d) { return (d->R * d->S * d->C + 7) / 8 
 
 int launch_im2col(const B2ConvDesc* d, const void* x, const float* mask, bf16* col, cudaStream_t st) {
   const int kpad = stem_kpad(d);
-  long long total = (long long)d->N * d->Ho * d->Wo * (kpad / 8);
-  long long want = (total + 255) / 256, cap = (long long)b2_num_sms() * 16;
-  int grid = (int)(want > cap ? cap : want);
-  im2col_kernel<<<grid, 256, 0, st>>>((const bf16*)x, mask, col, d->N, d->H, d->W, d->C, d->R, d->S, d->stride, d->pad,
-                                      d->dil, d->Ho, d->Wo, kpad);
+  const size_t sh = (size_t)d->R * (d->W + 2 * d->pad) * d->C * sizeof(float);
+  B2_REQUIRE(sh <= 200 * 1024, B2_E_UNSUPPORTED, "im2col: input row too wide for shared memory");
+  if (sh > 48 * 1024) cudaFuncSetAttribute(im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+  im2col_kernel<<<d->N * d->Ho, 256, sh, st>>>((const bf16*)x, mask, col, d->N, d->H, d->W, d->C, d->R, d->S, d->stride,
+                                             d->pad, d->dil, d->Ho, d->Wo, kpad);
   B2_LAUNCH_CHECK("im2col");
   return B2_OK;
 }
@@ -730,7 +858,7 @@ size_t conv_tc_workspace_bytes(const B2ConvDesc* d, int op) {
 }
 
 int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, const void* w, const float* bias,
-                  void* y, float* mask_out, float* ratio_out, double* bn_sums, void* workspace, cudaStream_t st) {
+                  void* y, float* mask_out, float* ratio_out, float* bn_sums, void* workspace, cudaStream_t st) {
   RunArgs a{};
   const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
   a.act = x; a.N = d->N; a.H = d->H; a.W = d->W; a.C = d->C;
@@ -750,9 +878,11 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   a.mask_in = mask_in; a.bias = bias; a.mask_out = mask_out; a.ratio_out = ratio_out;
   a.mask_R = d->R; a.mask_S = d->S; a.mask_stride = d->stride; a.mask_pad = d->pad; a.mask_dil = d->dil;
   a.mask_H = d->H; a.mask_W = d->W;
+  bool fused = false;
+  a.bn_sums = bn_sums; a.stats_fused = &fused;
   int rc = run_conv_tc(a, st);
   if (rc) return rc;
-  if (bn_sums) return b2_bn_stats(y, (int64_t)d->N * d->Ho * d->Wo, d->K, d->dtype, bn_sums, (void*)st);
+  if (bn_sums && !fused) return b2_bn_stats(y, (int64_t)d->N * d->Ho * d->Wo, d->K, d->dtype, bn_sums, (void*)st);
   return B2_OK;
 }
 

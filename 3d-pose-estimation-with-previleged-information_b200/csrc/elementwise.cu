@@ -119,6 +119,15 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict_
     if (c < C && p < HW) out[((long long)n * HW + p) * C + c] = from_f<T>(tile[threadIdx.x][i]);
   }
 }
+// few channels (network inputs, C <= 4): one thread per pixel, plane reads and pixel writes both coalesced
+template <typename T, int C>
+__global__ void nchw_to_nhwc_small_kernel(const float* __restrict__ in, T* __restrict__ out, long long HW, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i - n * HW;
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[i * C + c] = from_f<T>(in[(n * C + c) * HW + p]);
+  }
+}
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int C, long long HW) {
   __shared__ float tile[32][33];
@@ -332,6 +341,17 @@ extern "C" int b2_nchw_to_nhwc(const float* in, void* out, int32_t N, int32_t C,
   B2_REQUIRE(N <= 65535, B2_E_UNSUPPORTED, "nchw_to_nhwc: N > 65535");
   cudaStream_t st = (cudaStream_t)stream;
   long long HW = (long long)H * W;
+  if (C <= 4) {
+    const long long total = HW * N;
+    const int g = grid_for(total, 256);
+#define SMALL_C(CC)                                                                                            \
+  if (dtype == B2_F32) nchw_to_nhwc_small_kernel<float, CC><<<g, 256, 0, st>>>(in, (float*)out, HW, total);  \
+  else nchw_to_nhwc_small_kernel<bf16, CC><<<g, 256, 0, st>>>(in, (bf16*)out, HW, total);
+    if (C == 1) { SMALL_C(1) } else if (C == 2) { SMALL_C(2) } else if (C == 3) { SMALL_C(3) } else { SMALL_C(4) }
+#undef SMALL_C
+    B2_LAUNCH_CHECK("nchw_to_nhwc");
+    return B2_OK;
+  }
   dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
   if (dtype == B2_F32) nchw_to_nhwc_kernel<float><<<grid, block, 0, st>>>(in, (float*)out, C, HW);
   else nchw_to_nhwc_kernel<bf16><<<grid, block, 0, st>>>(in, (bf16*)out, C, HW);

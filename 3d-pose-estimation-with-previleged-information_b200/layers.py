@@ -35,6 +35,7 @@ class _B2ConvBase(nn.Conv2d):
         self._d = _square(self.dilation, "dilation")
         self.weight.data = self.weight.data.contiguous(memory_format=torch.channels_last)
         self._shadow = None           # bf16 KRSC copy maintained by the Trainer's fused Adam step
+        self._grad_sink = None        # [K,C,R,S] view of the Trainer's flat gradient buffer
 
     def shadow(self, dtype):
         s = self._shadow
@@ -99,6 +100,7 @@ class BatchNorm2d(nn.BatchNorm2d):
     num_batches_tracked for all layers with one foreach op outside the captured graph."""
 
     defer_count = False
+    _grad_sinks = None      # (gamma.grad, beta.grad) views of the Trainer's flat gradient buffer
 
     def tick(self):
         if self.training and self.track_running_stats and not self.defer_count:
@@ -114,7 +116,10 @@ def conv_bn(x, veil, conv, bn, relu, residual=None, mask_output=False, premasked
     training = bn.training
     cfg = (conv._s, conv._p, conv._d, partial, premasked and partial, relu, mask_output and partial, training,
            0.1 if bn.momentum is None else bn.momentum, bn.eps, conv.force_ffma)
+    sinks = None
+    if conv._grad_sink is not None and bn._grad_sinks is not None and torch.is_grad_enabled():
+        sinks = (conv._grad_sink,) + bn._grad_sinks
     z, vout = ops.ConvBNFn.apply(x, veil if partial else None, conv.weight, conv.shadow(x.dtype), bn.weight,
-                                 bn.bias, bn.running_mean, bn.running_var, residual, cfg)
+                                 bn.bias, bn.running_mean, bn.running_var, residual, cfg, sinks)
     bn.tick()
     return z, (vout if partial else veil)

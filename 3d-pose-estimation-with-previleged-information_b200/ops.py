@@ -30,6 +30,11 @@ def make_desc(xshape, K, R, S, stride, pad, dil, dtype, flags):
 _workspaces = {}
 
 
+def bn_partials(C, device):
+    """Uninitialised partial-sum buffer float[BN_PARTS][2C] (the producers write every slot)."""
+    return torch.empty(L.BN_PARTS * 2 * C, dtype=torch.float32, device=device)
+
+
 def workspace(nbytes, device):
     """Grow-only scratch buffer per (device, stream)."""
     if nbytes == 0:
@@ -93,7 +98,7 @@ def _conv_fprop(desc, x, mask, wk, bias, want_ratio, want_stats):
     partial = bool(desc.flags & L.CONV_PARTIAL)
     mask_out = torch.empty((desc.N, desc.Ho, desc.Wo), dtype=torch.float32, device=dev) if partial else None
     ratio = torch.empty_like(mask_out) if (partial and want_ratio) else None
-    sums = torch.zeros(2 * desc.K, dtype=torch.float64, device=dev) if want_stats else None
+    sums = bn_partials(desc.K, dev) if want_stats else None
     ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 0), dev)
     L.call("b2_pconv_fprop", C.byref(desc), L.ptr(x), L.ptr(mask), L.ptr(wk), L.ptr(bias), L.ptr(y),
            L.ptr(mask_out), L.ptr(ratio), L.ptr(sums), L.ptr(ws), wsn, L.stream())
@@ -109,13 +114,20 @@ def _conv_dgrad(desc, dy, ratio, wk, mask):
     return dx
 
 
-def _conv_wgrad(desc, x, mask, dy, ratio):
+def _conv_wgrad(desc, x, mask, dy, ratio, sink=None):
+    """dw (fp32, KRSC) accumulated into ``sink`` (a [K,C,R,S] channels_last view of the flat gradient
+    buffer; returns None) or into a fresh zero tensor (returned as logical [K,C,R,S])."""
     dev = dy.device
-    dw = torch.zeros((desc.K, desc.R, desc.S, desc.C), dtype=torch.float32, device=dev)
+    if sink is not None:
+        dw = sink.permute(0, 2, 3, 1)
+        if not dw.is_contiguous() or dw.dtype != torch.float32:
+            raise RuntimeError("gradient sink must be an fp32 channels_last view")
+    else:
+        dw = torch.zeros((desc.K, desc.R, desc.S, desc.C), dtype=torch.float32, device=dev)
     ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 2), dev)
     L.call("b2_pconv_wgrad", C.byref(desc), L.ptr(x), L.ptr(mask), L.ptr(dy), L.ptr(ratio), L.ptr(dw),
            L.ptr(ws), wsn, L.stream())
-    return dw.permute(0, 3, 1, 2)      # logical [K,C,R,S], channels_last memory
+    return None if sink is not None else dw.permute(0, 3, 1, 2)
 
 
 # --------------------------------------------------------------------------- convolution
@@ -177,7 +189,7 @@ class ConvBNFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, mask, weight, shadow, gamma, beta, running_mean, running_var, residual, cfg):
+    def forward(ctx, x, mask, weight, shadow, gamma, beta, running_mean, running_var, residual, cfg, sinks=None):
         stride, pad, dil, partial, premasked, relu, mask_output, training, momentum, eps, force_ffma = cfg
         L.require_cuda(x, mask, weight, gamma)
         x = x.contiguous()
@@ -196,43 +208,56 @@ class ConvBNFn(Function):
         if residual is not None:
             residual = residual.contiguous()
         row_mask = mask_out if (mask_output and partial) else None
-        L.call("b2_bn_apply", L.ptr(y), L.ptr(sums), L.ptr(gamma), L.ptr(beta), L.ptr(running_mean),
-               L.ptr(running_var), float(momentum), float(eps), int(training), L.ptr(residual), L.ptr(row_mask),
-               int(relu), L.ptr(z), L.ptr(mean), L.ptr(invstd), rows, K, L.dt(y), L.stream())
+        L.call("b2_bn_finalize", L.ptr(sums), rows, K, L.ptr(running_mean), L.ptr(running_var), float(momentum),
+               float(eps), int(training), L.ptr(mean), L.ptr(invstd), L.stream())
+        L.call("b2_bn_apply", L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma), L.ptr(beta), L.ptr(residual),
+               L.ptr(row_mask), int(relu), L.ptr(z), rows, K, L.dt(y), L.stream())
         ctx.desc, ctx.relu, ctx.training, ctx.wdtype = desc, relu, training, weight.dtype
         ctx.has_res = residual is not None
-        ctx.save_for_backward(x, mask if partial else None, wk, ratio, y, z, mean, invstd, gamma.detach(),
-                              row_mask if not relu else None)
+        ctx.sinks = sinks
+        # z is only needed for the ReLU gate of residual layers; otherwise the gate is recomputed from y
+        ctx.save_for_backward(x, mask if partial else None, wk, ratio, y, z if (relu and residual is not None) else None,
+                              mean, invstd, gamma.detach(), beta.detach(), row_mask)
         if partial:
             ctx.mark_non_differentiable(mask_out)
         return z, mask_out
 
     @staticmethod
     def backward(ctx, dz, _dmask):
-        x, mask, wk, ratio, y, z, mean, invstd, gamma, row_mask = ctx.saved_tensors
+        x, mask, wk, ratio, y, z, mean, invstd, gamma, beta, row_mask = ctx.saved_tensors
         desc = ctx.desc
         dz = dz.contiguous()
         dev = dz.device
         K, rows = desc.K, desc.N * desc.Ho * desc.Wo
-        sums = torch.zeros(2 * K, dtype=torch.float64, device=dev)
-        L.call("b2_bn_bwd_reduce", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(row_mask),
-               int(ctx.relu), L.ptr(sums), rows, K, L.dt(dz), L.stream())
+        sinks = ctx.sinks
+        parts = bn_partials(K, dev)
+        L.call("b2_bn_bwd_reduce", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+               L.ptr(beta), L.ptr(row_mask), int(ctx.relu), L.ptr(parts), rows, K, L.dt(dz), L.stream())
         dy = torch.empty_like(y)
         dres = torch.empty_like(y) if (ctx.has_res and ctx.needs_input_grad[8]) else None
-        dgamma = torch.zeros(K, dtype=torch.float32, device=dev)
-        dbeta = torch.zeros(K, dtype=torch.float32, device=dev)
+        if sinks is not None:
+            dgamma, dbeta = sinks[1], sinks[2]            # accumulate straight into the flat gradient buffer
+        else:
+            dgamma = torch.zeros(K, dtype=torch.float32, device=dev)
+            dbeta = torch.zeros(K, dtype=torch.float32, device=dev)
+        gsum = torch.empty(2 * K, dtype=torch.float32, device=dev)
+        L.call("b2_bn_bwd_finalize", L.ptr(parts), K, L.ptr(gsum), L.ptr(dgamma), L.ptr(dbeta), L.stream())
         L.call("b2_bn_bwd_apply", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
-               L.ptr(sums), L.ptr(row_mask), L.ptr(ratio), int(ctx.relu), int(ctx.training), L.ptr(dy),
-               L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), rows, K, L.dt(dz), L.stream())
+               L.ptr(beta), L.ptr(gsum), L.ptr(row_mask), L.ptr(ratio), int(ctx.relu), int(ctx.training), L.ptr(dy),
+               L.ptr(dres), rows, K, L.dt(dz), L.stream())
         # dy now holds dRaw = dOut * ratio -> tell the conv kernels not to scale again
         desc.flags |= L.CONV_DY_PRESCALED
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = _conv_dgrad(desc, dy, None, wk, mask)
         if ctx.needs_input_grad[2]:
-            dw = _conv_wgrad(desc, x, mask, dy, None).to(ctx.wdtype)
+            dw = _conv_wgrad(desc, x, mask, dy, None, sinks[0] if sinks is not None else None)
+            if dw is not None:
+                dw = dw.to(ctx.wdtype)
         desc.flags &= ~L.CONV_DY_PRESCALED
-        return dx, None, dw, None, dgamma, dbeta, None, None, dres, None
+        if sinks is not None:
+            dgamma = dbeta = None
+        return dx, None, dw, None, dgamma, dbeta, None, None, dres, None, None
 
 
 class MaxPoolFn(Function):

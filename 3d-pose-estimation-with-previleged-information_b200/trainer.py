@@ -95,8 +95,10 @@ class _FlatState:
                 self.w[o:o + n].copy_(src)
                 p.data = self.w[o:o + n].view(K, R, S, Cc).permute(0, 3, 1, 2)
                 p.grad = self.g[o:o + n].view(K, R, S, Cc).permute(0, 3, 1, 2)
-                if want_shadow and id(p) in owner:
-                    owner[id(p)]._shadow = self.w16[o:o + n].view(K, R, S, Cc)
+                if id(p) in owner:
+                    owner[id(p)]._grad_sink = p.grad
+                    if want_shadow:
+                        owner[id(p)]._shadow = self.w16[o:o + n].view(K, R, S, Cc)
             else:
                 self.w[o:o + n].copy_(p.data.view(-1).float())
                 p.data = self.w[o:o + n].view(p.shape)
@@ -144,6 +146,7 @@ class Trainer:
         self.bns = [m for m in model.modules() if isinstance(m, BatchNorm2d)]
         for m in self.bns:
             m.defer_count = True
+            m._grad_sinks = (m.weight.grad, m.bias.grad)
         self.lr = self.learn_rate
         self.step_count = 0
         self.betas, self.eps = (0.9, 0.999), 1e-8

@@ -27,7 +27,10 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 1
+#define B2_ABI_VERSION 2
+
+/* slots of a BatchNorm partial-sum buffer: float[B2_BN_PARTS][2*C] (see the BatchNorm section) */
+#define B2_BN_PARTS 320
 
 enum { B2_F32 = 0, B2_BF16 = 1 };
 
@@ -73,10 +76,11 @@ size_t b2_conv_workspace_bytes(const B2ConvDesc* d, int op);
  *   y = conv(x*mask_in, w) * ratio                      (no bias, :53)
  *   y = (conv(x*mask_in, w) * ratio + bias) * mask_out  (bias, :49-51)
  * mask_in/mask_out/ratio_out are fp32; ratio_out (optional) saves the per-pixel factor for
- * the backward pass.  bias is fp32 [K] or NULL.  bn_sums (optional, double[2*K], caller
- * zeroes) receives per-channel sum / sum-of-squares of the stored y for training BatchNorm. */
+ * the backward pass.  bias is fp32 [K] or NULL.  bn_partials (optional, float[B2_BN_PARTS][2*K])
+ * receives the per-channel partial sums / sums of squares of the stored y for training BatchNorm
+ * (fused into the tensor-core epilogue where possible, else a b2_bn_stats pass). */
 int b2_pconv_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, const void* w,
-                   const float* bias, void* y, float* mask_out, float* ratio_out, double* bn_sums,
+                   const float* bias, void* y, float* mask_out, float* ratio_out, float* bn_partials,
                    void* workspace, size_t ws_bytes, void* stream);
 
 /* backward of the above w.r.t. x (autograd of partial_conv.py:46-53):
@@ -113,27 +117,35 @@ int b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* ---- BatchNorm2d (+ReLU, +residual, +veil) --------------------------------------------
  * replaces nn.BatchNorm2d / F.relu / residual add in the blocks, partial_depthnet.py:143-157,
  * fusionnet.py:107-127,138-140.  Training statistics are per call (per rank), momentum
- * update of running stats as torch (unbiased variance). */
-/* sums[0:C] += sum_r y, sums[C:2C] += sum_r y^2  (double) */
-int b2_bn_stats(const void* y, int64_t rows, int32_t C, int32_t dtype, double* sums, void* stream);
-/* z = relu?( (y-mean)*invstd*gamma + beta (+ residual) ) (* row_mask[r])
- * training != 0: mean/var from `sums` (count = rows), running stats updated, save_mean /
- * save_invstd written; training == 0: mean/var from running stats. */
-int b2_bn_apply(const void* y, const double* sums, const float* gamma, const float* beta,
-                float* running_mean, float* running_var, float momentum, float eps, int32_t training,
-                const void* residual, const float* row_mask, int32_t relu, void* z, float* save_mean,
-                float* save_invstd, int64_t rows, int32_t C, int32_t dtype, void* stream);
-/* backward, pass 1: g = dz * (relu ? z>0 : 1) (* row_mask);  sums[0:C] += sum g,
- * sums[C:2C] += sum g * xhat. */
+ * update of running stats as torch (unbiased variance).
+ *
+ * Per-channel reductions are atomics-free and deterministic: a producer (b2_bn_stats, the fused
+ * epilogue of b2_pconv_fprop, b2_bn_bwd_reduce) writes fp32 partial sums to its own slot of
+ * `partials` = float[B2_BN_PARTS][2*C] (every slot is written, unused ones with zeros, so the
+ * buffer needs no initialisation) and a finalize call combines the slots in fp64. */
+/* partials[slot][0:C] = sum_r y, partials[slot][C:2C] = sum_r y^2 over the slot's rows */
+int b2_bn_stats(const void* y, int64_t rows, int32_t C, int32_t dtype, float* partials, void* stream);
+/* training != 0: mean / biased var from `partials` (count = rows), running stats updated;
+ * training == 0: from the running stats.  Writes mean[C], invstd[C]. */
+int b2_bn_finalize(const float* partials, int64_t rows, int32_t C, float* running_mean, float* running_var,
+                   float momentum, float eps, int32_t training, float* mean, float* invstd, void* stream);
+/* z = relu?( (y-mean)*invstd*gamma + beta (+ residual) ) (* row_mask[r]) */
+int b2_bn_apply(const void* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                const void* residual, const float* row_mask, int32_t relu, void* z, int64_t rows, int32_t C,
+                int32_t dtype, void* stream);
+/* backward, pass 1: g = dz * (relu ? z>0 : 1) (* row_mask);  partial sums of g and g * xhat.
+ * z may be NULL for a layer WITHOUT residual: the ReLU gate is then recomputed from y, gamma, beta
+ * with the forward's own fp32 expression (saves reading z). */
 int b2_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                     const float* row_mask, int32_t relu, double* sums, int64_t rows, int32_t C,
-                     int32_t dtype, void* stream);
+                     const float* gamma, const float* beta, const float* row_mask, int32_t relu, float* partials,
+                     int64_t rows, int32_t C, int32_t dtype, void* stream);
+/* gsum[0:C] = sum g, gsum[C:2C] = sum g*xhat;  dgamma += sum g*xhat, dbeta += sum g (fp32, accumulated) */
+int b2_bn_bwd_finalize(const float* partials, int32_t C, float* gsum, float* dgamma, float* dbeta, void* stream);
 /* backward, pass 2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) (* row_scale[r]);
- * d_residual = g (optional); dgamma += sum g*xhat, dbeta += sum g (fp32, accumulated).
- * training == 0 (frozen statistics): dy = gamma*invstd*g. */
+ * d_residual = g (optional).  training == 0 (frozen statistics): dy = gamma*invstd*g. */
 int b2_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                    const float* gamma, const double* sums, const float* row_mask, const float* row_scale,
-                    int32_t relu, int32_t training, void* dy, void* d_residual, float* dgamma, float* dbeta,
+                    const float* gamma, const float* beta, const float* gsum, const float* row_mask,
+                    const float* row_scale, int32_t relu, int32_t training, void* dy, void* d_residual,
                     int64_t rows, int32_t C, int32_t dtype, void* stream);
 
 /* ---- MaxPool2d(3, stride 2, pad 1) on x and veil together: partial_depthnet.py:219-220 --- */

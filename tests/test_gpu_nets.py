@@ -95,7 +95,7 @@ def test_net_and_step_fp32(b2pose, dev, golden_dir, tag):
     # first update is ~lr*sign(g), i.e. rounding noise decides the direction for near-zero
     # gradients -- so the second step is only reproducible to a looser bound (any two BLAS differ so).
     np.testing.assert_allclose(losses[0], g[f"{tag}_loss"][0], rtol=1e-4)
-    np.testing.assert_allclose(gns[0], g[f"{tag}_gradnorm"][0], rtol=2e-3)
+    np.testing.assert_allclose(gns[0], g[f"{tag}_gradnorm"][0], rtol=5e-3)
     np.testing.assert_allclose(losses[1], g[f"{tag}_loss"][1], rtol=1e-2)
     np.testing.assert_allclose(gns[1], g[f"{tag}_gradnorm"][1], rtol=1e-1)
     sd = net.state_dict()
