@@ -135,10 +135,14 @@ __device__ __forceinline__ void slot_sums(const float* __restrict__ partials, in
   const int l = threadIdx.y;
   double s = 0.0, q = 0.0;
   if (c < C) {
-    for (int i = l; i < B2_BN_PARTS; i += 8) {
-      s += (double)partials[(size_t)i * 2 * C + c];
-      q += (double)partials[(size_t)i * 2 * C + C + c];
+    float ps[B2_BN_PARTS / 8], pq[B2_BN_PARTS / 8];
+#pragma unroll
+    for (int i = 0; i < B2_BN_PARTS / 8; ++i) {            // 40 independent loads each, then the fp64 sums
+      ps[i] = partials[(size_t)(l + 8 * i) * 2 * C + c];
+      pq[i] = partials[(size_t)(l + 8 * i) * 2 * C + C + c];
     }
+#pragma unroll
+    for (int i = 0; i < B2_BN_PARTS / 8; ++i) { s += (double)ps[i]; q += (double)pq[i]; }
   }
   sm[0][l][threadIdx.x] = s;
   sm[1][l][threadIdx.x] = q;
