@@ -6,13 +6,14 @@ and the only per-step exchange is the gradient all-reduce over the flat gradient
 bound, so a few large buckets are right).  The sum is turned into the mean inside the fused
 Adam kernel (inv_scale = 1/world), so no separate divide pass touches the gradients.
 """
+import datetime
 import os
 
 import torch
 import torch.distributed as dist
 
 
-def init_from_env(backend=None):
+def init_from_env(backend=None, timeout_s=180):
     """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / MASTER_*)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -24,9 +25,11 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local),
+                                    timeout=datetime.timedelta(seconds=timeout_s))
         else:
-            dist.init_process_group(backend, rank=rank, world_size=world)
+            dist.init_process_group(backend, rank=rank, world_size=world,
+                                    timeout=datetime.timedelta(seconds=timeout_s))
     return rank, local, world
 
 

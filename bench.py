@@ -297,20 +297,23 @@ def run_b200(args):
             ms = float(t)
         return ms, last
 
+    # every rank runs the same number of steps (collectives must line up); rank 0 also samples clocks
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)          # let nvidia-smi start; the first rows are idle-clock samples
-        for _ in range(3):
-            trainer.train_step(resident)
-        torch.cuda.synchronize()
+    for _ in range(3):
+        trainer.train_step(resident)
+    barrier()
+    if rank == 0:
         sampler.rows.clear()
     ms_dev, out = timed(resident, False)
-    if rank == 0 and ms_dev < 1500.0:   # keep the GPU under the same load until a few samples exist
-        t_end = time.perf_counter() + 1.5
-        while time.perf_counter() < t_end:
-            trainer.train_step(resident)
-        torch.cuda.synchronize()
+    # keep the GPUs under the same load until a few clock samples exist (count derived from the
+    # all-reduced time, so it is identical on every rank)
+    extra = 0 if ms_dev >= 1500.0 else min(200, int(1500.0 / max(ms_dev / args.steps, 0.1)))
+    for _ in range(extra):
+        trainer.train_step(resident)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, out2 = timed(host, True)
     loss = float(out2["loss"])
