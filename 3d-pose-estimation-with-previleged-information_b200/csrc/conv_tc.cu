@@ -4,8 +4,8 @@
 //   dgrad : the same kernel run on dy with the filter flipped/transposed (stride-1 layers)
 //   wgrad : D[k, (tap, c)] = sum over pixels of dY[pixel, k] * X[pixel shifted by tap, c]  (MN-major operands)
 //
-// One persistent CTA per SM (192 threads): warp 0 is the TMA producer, warp 1 issues tcgen05.mma
-// (one elected lane), warps 2-5 are the epilogue (each owns the 32 TMEM lanes of its warp-id
+// One persistent CTA per SM (320 threads; 192 in the wgrad kernel): warp 0 is the TMA producer, warp 1 issues tcgen05.mma
+// (one elected lane), warps 2-9 are the epilogue (two warps share the 32 TMEM lanes of a warp-id
 // quarter).  Activation tiles are fetched with 4-D *tiled* TMA boxes (C, W, H, N): a tile of
 // output pixels is a BNIxBHxBW brick, and for filter tap (r, s) the A operand is that brick
 // shifted by (r*dil - pad, s*dil - pad); out-of-bounds rows/columns (padding, ragged edges) are
@@ -24,7 +24,8 @@
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;          // wgrad kernel: producer, MMA, 4 epilogue warps
+constexpr int kConvThreads = 320;      // fprop/dgrad kernel: producer, MMA, 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int kMaxStages = 8;
 constexpr int kTileM = 128;          // UMMA M (output pixels per tile / TMEM lanes)
 constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
@@ -88,7 +89,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -153,6 +154,7 @@ struct FpropParams {
   int out_stride_sp, out_off_h, out_off_w;             // strided dgrad: row (oh, ow) is stored at (oh*sp+off_h, ow*sp+off_w)
   int out_H, out_W;                                    // spatial size of the tensor written
   int tma_store;                                       // epilogue: smem-staged TMA store (+ fused BN statistics)
+  int debug;                                           // tuning experiments (B2POSE_TC_DEBUG): 1 skip epilogue, 2 skip store, 4 skip B reload
   float* bn_sums;                                      // partials[B2_BN_PARTS][2*K]: sum / sum of squares of the stored output
 };
 
@@ -161,7 +163,7 @@ struct __align__(8) PipeBars {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -172,9 +174,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // layout: [stages][A|B] | kStaging x 16 KB output staging (TMA-store epilogue) | barriers | fp32 statistics [2*K]
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
   PipeBars* bars = reinterpret_cast<PipeBars*>(staging + (p.tma_store ? kStaging * kABytes : 0));
-  float* s_stats = reinterpret_cast<float*>(bars + 1);
-  if (p.bn_sums)      // [4 epilogue warps][2*K]: warp-private partials, no shared atomics
-    for (int i = threadIdx.x; i < 8 * p.K; i += kThreads) s_stats[i] = 0.f;
+  float* s_stats = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~(uintptr_t)15);
+  if (p.bn_sums)      // [8 epilogue warps][2*K]: warp-private partials, no shared atomics
+    for (int i = threadIdx.x; i < 16 * p.K; i += kConvThreads) s_stats[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
@@ -182,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 8); }
     fence_barrier_init();
     prefetch_map(&map_a);
     prefetch_map(&map_b);
@@ -245,12 +247,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter: warp (q, half) owns rows 32q..32q+31 and the `half` 32-column
+    // part of every 64-column group.
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;
+    const int ew = warp - 2;                      // epilogue warp index 0..7
+    const int ep_tid = threadIdx.x - 64;          // 0..255
     const int row = q * 32 + lane;
     const int brick = p.BW * p.BH;
+    const int groups = p.BN >> 6;
+    const int nsets = p.tma_store ? kStaging / groups : 1;      // staging sets of `groups` 16 KB buffers
     int local = 0;
-    int ep_group = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -279,7 +287,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           scale = pconv_ratio((float)(p.mask_R * p.mask_S), cnt);
           mo = fminf(fmaxf(cnt, 0.f), 1.f);
-          if (kt == 0) {
+          if (kt == 0 && half == 0) {
             if (p.mask_out) p.mask_out[pix] = mo;
             if (p.ratio_out) p.ratio_out[pix] = scale;
           }
@@ -291,53 +299,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
       const int kbase = kt * p.BN;
+      if (p.debug & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+        continue;
+      }
       if (p.tma_store) {
-        // ---- smem-staged epilogue: 64-column groups -> swizzled staging tile -> TMA store; the
-        //      staged (rounded) values also feed the per-channel BatchNorm statistics.
-        const int ep_tid = threadIdx.x - 64;
-        const int groups = p.BN >> 6;
+        // ---- smem-staged epilogue: the whole tile goes to `groups` swizzled 16 KB staging buffers
+        //      (one per 64 output channels), then one thread issues the TMA stores; the staged
+        //      (rounded) values also feed the per-channel BatchNorm partial sums.
+        uint8_t* sset = staging + (size_t)((local % nsets) * groups) * kABytes;
+        if (ep_tid == 0) {                       // the stores issued `nsets` tiles ago have drained this set
+          if (nsets >= 4) bulk_wait_read<3>();
+          else if (nsets == 2) bulk_wait_read<1>();
+          else bulk_wait_read<0>();
+        }
+        epi_barrier();
+        // software-pipelined TMEM reads: the loads of group g+1 are in flight while group g is converted
+        uint32_t va[32], vb[32];
+        tmem_ld16(taddr + half * 32, va);
+        tmem_ld16(taddr + half * 32 + 16, va + 16);
         for (int g = 0; g < groups; ++g) {
-          uint8_t* sbuf = staging + (size_t)(ep_group & (kStaging - 1)) * kABytes;
-          ++ep_group;
-          if (ep_tid == 0) bulk_wait_read<kStaging - 1>();   // the store issued kStaging groups ago has drained this buffer
-          epi_barrier();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld16(taddr + g * 64 + h * 32, v);
-            tmem_ld16(taddr + g * 64 + h * 32 + 16, v + 16);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = valid ? __uint_as_float(v[j * 8 + e]) * scale : 0.f;
-              const int chunk = h * 4 + j;
-              store8(reinterpret_cast<bf16*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)), f);
-            }
+          uint32_t* v = (g & 1) ? vb : va;
+          uint32_t* vn = (g & 1) ? va : vb;
+          tmem_ld_wait();
+          if (g + 1 < groups) {
+            tmem_ld16(taddr + (g + 1) * 64 + half * 32, vn);
+            tmem_ld16(taddr + (g + 1) * 64 + half * 32 + 16, vn + 16);
           }
-          if (g == groups - 1) {                          // accumulator fully read: hand TMEM back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+          uint8_t* sbuf = sset + (size_t)g * kABytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = valid ? __uint_as_float(v[j * 8 + e]) * scale : 0.f;
+            const int chunk = half * 4 + j;
+            store8(reinterpret_cast<bf16*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)), f);
           }
-          fence_async_smem();
-          epi_barrier();
-          if (ep_tid == 0) {
-            tma_store_4d(&map_out, smem_u32(sbuf), kbase + g * 64, wi * p.BW, hi * p.BH, ni * p.BNI);
-            bulk_commit();
-          }
-          if (p.bn_sums) {
-            // per-channel sum / sum of squares of the staged (bf16-rounded) tile: 16-byte shared loads
-            // (a quarter-warp reads one whole 128-byte row), two shuffle steps, 8 lanes x 16 shared atomics
-            const int chunk = ep_tid & 7, rsub = ep_tid >> 3;
-            const int nrows = min(brick * p.BNI, kTileM);
+        }
+        tc_fence_before();                        // accumulator fully read: hand TMEM back to the MMA warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+        fence_async_smem();
+        epi_barrier();
+        if (ep_tid == 0 && !(p.debug & 2)) {
+          for (int g = 0; g < groups; ++g)
+            tma_store_4d(&map_out, smem_u32(sset + (size_t)g * kABytes), kbase + g * 64, wi * p.BW, hi * p.BH,
+                         ni * p.BNI);
+          bulk_commit();
+        }
+        if (p.bn_sums) {
+          // per-channel sum / sum of squares of the staged tile: 16-byte shared loads (a quarter-warp
+          // reads one whole 128-byte row), two shuffle steps, warp-private fp32 accumulators
+          const int chunk = ep_tid & 7, rsub = ep_tid >> 3;        // rsub 0..31
+          const int nrows = min(brick * p.BNI, kTileM);
+          float* mine = s_stats + (size_t)ew * 2 * p.K;
+          for (int g = 0; g < groups; ++g) {
+            const uint8_t* sbuf = sset + (size_t)g * kABytes;
             float su[8], sq[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) su[e] = sq[e] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = rsub + 16 * i;
+            for (int i = 0; i < 4; ++i) {
+              const int r = rsub + 32 * i;
               if (r < nrows) {
                 float t[8];
                 load8(reinterpret_cast<const bf16*>(sbuf + r * 128 + ((chunk ^ (r & 7)) << 4)), t);
@@ -353,19 +378,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
             }
             const int ch0 = kbase + g * 64 + chunk * 8;
-            if (lane < 8 && ch0 < p.K) {
-              float* mine = s_stats + (size_t)q * 2 * p.K;       // q = this warp's quarter
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                mine[ch0 + e] += su[e];
-                mine[p.K + ch0 + e] += sq[e];
-              }
+            if (lane < 8 && ch0 < p.K) {           // 16-byte read-modify-writes of the warp-private partials
+              float4* ps = reinterpret_cast<float4*>(mine + ch0);
+              float4* pq = reinterpret_cast<float4*>(mine + p.K + ch0);
+              float4 s0 = ps[0], s1 = ps[1], q0 = pq[0], q1 = pq[1];
+              s0.x += su[0]; s0.y += su[1]; s0.z += su[2]; s0.w += su[3];
+              s1.x += su[4]; s1.y += su[5]; s1.z += su[6]; s1.w += su[7];
+              q0.x += sq[0]; q0.y += sq[1]; q0.z += sq[2]; q0.w += sq[3];
+              q1.x += sq[4]; q1.y += sq[5]; q1.z += sq[6]; q1.w += sq[7];
+              ps[0] = s0; ps[1] = s1; pq[0] = q0; pq[1] = q1;
             }
           }
         }
         continue;
       }
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      // ---- direct-store epilogue (ragged channel tiles, strided scatter of dgrad)
+      for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
         uint32_t v[32];
         const bool two = (c0 + 16) < p.BN;
         tmem_ld16(taddr + c0, v);
@@ -401,10 +429,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   if (p.bn_sums) {      // this CTA's slot of partials[B2_BN_PARTS][2K]; the unused slots are zero-filled
     float* slot = p.bn_sums + (size_t)blockIdx.x * 2 * p.K;
-    for (int i = threadIdx.x; i < 2 * p.K; i += kThreads)
-      slot[i] = (s_stats[i] + s_stats[2 * p.K + i]) + (s_stats[4 * p.K + i] + s_stats[6 * p.K + i]);
+    for (int i = threadIdx.x; i < 2 * p.K; i += kConvThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_stats[(size_t)w * 2 * p.K + i];
+      slot[i] = t;
+    }
     for (int sl = gridDim.x + blockIdx.x; sl < B2_BN_PARTS; sl += gridDim.x)
-      for (int i = threadIdx.x; i < 2 * p.K; i += kThreads) p.bn_sums[(size_t)sl * 2 * p.K + i] = 0.f;
+      for (int i = threadIdx.x; i < 2 * p.K; i += kConvThreads) p.bn_sums[(size_t)sl * 2 * p.K + i] = 0.f;
   }
 }
 
@@ -415,27 +447,31 @@ struct WgradParams {
   int N, H, W, C, K, R, S, stride, pad, dil, Ho, Wo;
   int BW, BH, BNI;                 // pixel brick per pipeline stage (BW*BH*BNI = 64 pixels incl. ragged rows)
   int tiles_w, tiles_h, tiles_n;   // bricks over the OUTPUT pixel space
-  int BNc, ctiles, ktiles, splits; // columns per item, C/BNc, ceil(K/128), pixel splits
+  int BNc, ctiles, ktiles, splits; // columns per tap, ceil(C/BNc), ceil(K/128), pixel splits
+  int T, tgroups;                  // filter taps per work item (they share the dY tile), ceil(taps/T)
   int bricks_per_split;
   int stages, tmem_cols;
   float* dw;                       // [K][R*S][C] fp32
 };
 constexpr int kWgPix = 64;         // pixels per stage
 
+// Work item = (pixel split, tap group, c-tile, k-tile).  All T taps of a group read the same dY tile
+// (one TMA fetch) and their own shifted X tile; their accumulators sit side by side in TMEM.
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                 const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // stage: A = dy [2 atoms of 64 k][64 pix][128 B]  (16 KB), B = x [BNc/64 atoms][64 pix][128 B]
+  // stage: A = dy [2 atoms of 64 k][64 pix][128 B]  (16 KB), B = T x ( x [BNc/64 atoms][64 pix][128 B] )
   const uint32_t atom_bytes = kWgPix * 128;
   const uint32_t a_bytes = 2 * atom_bytes, b_bytes = (uint32_t)(p.BNc / 64) * atom_bytes;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)p.T * b_bytes;
   PipeBars* bars = reinterpret_cast<PipeBars*>(smem + (size_t)p.stages * stage_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.R * p.S;
-  const int total_items = p.splits * taps * p.ctiles * p.ktiles;
+  const int total_items = p.splits * p.tgroups * p.ctiles * p.ktiles;
   const int total_bricks = p.tiles_n * p.tiles_h * p.tiles_w;
+  const int acc_cols = p.T * p.BNc;          // TMEM columns of one accumulator set
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
@@ -451,10 +487,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   const uint32_t tmem_base = bars->tmem_base;
 
   // item decode: split fastest so CTAs running together share the same filter tile / spread pixels
-  auto decode = [&](int item, int& sp, int& tap, int& ct, int& kt) {
+  auto decode = [&](int item, int& sp, int& tg, int& ct, int& kt) {
     sp = item % p.splits; item /= p.splits;
     ct = item % p.ctiles; item /= p.ctiles;
-    tap = item % taps;    kt = item / taps;
+    tg = item % p.tgroups; kt = item / p.tgroups;
   };
 
   if (warp == 0) {
@@ -462,23 +498,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        int sp, tap, ct, kt;
-        decode(item, sp, tap, ct, kt);
-        const int r = tap / p.S, s = tap - r * p.S;
+        int sp, tg, ct, kt;
+        decode(item, sp, tg, ct, kt);
+        const int tap0 = tg * p.T, nt = min(p.T, taps - tap0);
         const int b0 = sp * p.bricks_per_split;
         const int b1 = min(total_bricks, b0 + p.bricks_per_split);
         for (int b = b0; b < b1; ++b) {
           const int wi = b % p.tiles_w, hi = (b / p.tiles_w) % p.tiles_h, ni = b / (p.tiles_w * p.tiles_h);
           const int ow0 = wi * p.BW, oh0 = hi * p.BH, n0 = ni * p.BNI;
           mbar_wait(&bars->empty[stage], phase ^ 1);
-          mbar_expect_tx(&bars->full[stage], stage_bytes);
+          mbar_expect_tx(&bars->full[stage], a_bytes + (uint32_t)nt * b_bytes);
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           // dy atoms: k channels [kt*128, +64) and [+64, +128)
           tma_load_4d(sa, &map_dy, &bars->full[stage], kt * 128, ow0, oh0, n0);
           tma_load_4d(sa + atom_bytes, &map_dy, &bars->full[stage], kt * 128 + 64, ow0, oh0, n0);
-          for (int a = 0; a < p.BNc / 64; ++a)
-            tma_load_4d(sa + a_bytes + a * atom_bytes, &map_x, &bars->full[stage], ct * p.BNc + a * 64,
-                        ow0 * p.stride - p.pad + s * p.dil, oh0 * p.stride - p.pad + r * p.dil, n0);
+          for (int j = 0; j < nt; ++j) {
+            const int tap = tap0 + j, r = tap / p.S, s = tap - r * p.S;
+            for (int a = 0; a < p.BNc / 64; ++a)
+              tma_load_4d(sa + a_bytes + j * b_bytes + a * atom_bytes, &map_x, &bars->full[stage],
+                          ct * p.BNc + a * 64, ow0 * p.stride - p.pad + s * p.dil,
+                          oh0 * p.stride - p.pad + r * p.dil, n0);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -489,26 +529,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     uint32_t phase = 0;
     int local = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++local) {
-      int sp, tap, ct, kt;
-      decode(item, sp, tap, ct, kt);
+      int sp, tg, ct, kt;
+      decode(item, sp, tg, ct, kt);
+      const int nt = min(p.T, taps - tg * p.T);
       const int b0 = sp * p.bricks_per_split;
       const int b1 = min(total_bricks, b0 + p.bricks_per_split);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&bars->tempty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BNc);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
       for (int b = b0; b < b1; ++b) {
         mbar_wait(&bars->full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           // MN-major, 128B swizzle: LBO = bytes between 64-element atoms along M/N, SBO = 1024 (8 pixel rows)
-          const uint64_t adesc = smem_desc(sa, atom_bytes, 1024), bdesc = smem_desc(sa + a_bytes, atom_bytes, 1024);
+          const uint64_t adesc = smem_desc(sa, atom_bytes, 1024);
+          for (int j = 0; j < nt; ++j) {
+            const uint64_t bdesc = smem_desc(sa + a_bytes + j * b_bytes, atom_bytes, 1024);
 #pragma unroll
-          for (int k = 0; k < kWgPix / 16; ++k)      // 16 pixels per MMA = 2 swizzle row groups = 2048 B
-            umma_bf16(tmem_d, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
-                      (uint32_t)((b - b0) | k));
+            for (int k = 0; k < kWgPix / 16; ++k)      // 16 pixels per MMA = 2 swizzle row groups = 2048 B
+              umma_bf16(tmem_d + (uint32_t)(j * p.BNc), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128),
+                        idesc, (uint32_t)((b - b0) | k));
+          }
           umma_commit(&bars->empty[stage]);
           if (b == b1 - 1) umma_commit(&bars->tfull[acc]);
         }
@@ -520,28 +564,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     const int q = warp & 3;
     int local = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++local) {
-      int sp, tap, ct, kt;
-      decode(item, sp, tap, ct, kt);
+      int sp, tg, ct, kt;
+      decode(item, sp, tg, ct, kt);
+      const int tap0 = tg * p.T, nt = min(p.T, taps - tap0);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&bars->tfull[acc], acc_phase);
       tc_fence_after();
       const int k = kt * 128 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BNc);
-      float* drow = p.dw + ((long long)k * taps + tap) * p.C + ct * p.BNc;
-      for (int c0 = 0; c0 < p.BNc; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld16(taddr + c0 + 16, v + 16);
-        tmem_ld_wait();
-        if (k < p.K) {
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols + j * p.BNc);
+        float* drow = p.dw + ((long long)k * taps + tap0 + j) * p.C + ct * p.BNc;
+        for (int c0 = 0; c0 < p.BNc; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + c0 + 16, v + 16);
+          tmem_ld_wait();
+          if (k < p.K) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)          // 16-byte vector reductions (C % 8 == 0 keeps groups whole)
-            if (ct * p.BNc + c0 + j < p.C)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + j),
-                           "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
-                           "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                           : "memory");
+            for (int jj = 0; jj < 32; jj += 4)       // 16-byte vector reductions (C % 8 == 0 keeps groups whole)
+              if (ct * p.BNc + c0 + jj < p.C)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + jj),
+                             "f"(__uint_as_float(v[jj])), "f"(__uint_as_float(v[jj + 1])),
+                             "f"(__uint_as_float(v[jj + 2])), "f"(__uint_as_float(v[jj + 3]))
+                             : "memory");
+          }
         }
       }
       tc_fence_before();
@@ -619,6 +666,66 @@ im2col_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* 
     store8(col + (pix0 + ow) * Kpad + ch * 8, f);
   }
 }
+// ---- 7x7 stride-2 stem as a 4x4 stride-1 convolution over a space-to-depth view ------------------
+// xs[n, h', w', (a*2+b)*C + c] = x[n, 2h'+a-1, 2w'+b-1, c] (* mask), channels >= 4C are zero.  With
+// pad' = 1 the tap (t, a) of the 4x4 view is the original tap r = 2t + a (r = 7 does not exist: zero
+// weight), so no im2col matrix is ever materialised: the view is 1/10 of its size.
+__global__ void s2d_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ xs, int N,
+                           int H, int W, int C, int H2, int W2, int Cp) {
+  const int chunks = Cp >> 3;
+  const long long total = (long long)N * H2 * W2 * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    const long long pix = i / chunks;
+    const int w2 = (int)(pix % W2);
+    const long long t = pix / W2;
+    const int h2 = (int)(t % H2), n = (int)(t / H2);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cc = ch * 8 + j;
+      float v = 0.f;
+      if (cc < 4 * C) {
+        const int ab = cc / C, c = cc - ab * C;
+        const int ih = 2 * h2 + (ab >> 1) - 1, iw = 2 * w2 + (ab & 1) - 1;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+          const long long ip = ((long long)n * H + ih) * W + iw;
+          v = __bfloat162float(x[ip * C + c]);
+          if (mask) v *= mask[ip];
+        }
+      }
+      f[j] = v;
+    }
+    store8(xs + pix * Cp + ch * 8, f);
+  }
+}
+// Ws[k][t][u][(a*2+b)*C + c] = W[k][2t+a][2u+b][c]  (zero where the 7x7 filter has no tap)
+__global__ void s2d_filter_kernel(const bf16* __restrict__ w, bf16* __restrict__ ws, int K, int C, int Cp) {
+  const int total = K * 16 * Cp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cc = i % Cp, tu = (i / Cp) % 16, k = i / (Cp * 16);
+    const int t = tu >> 2, u = tu & 3;
+    bf16 v = __float2bfloat16(0.f);
+    if (cc < 4 * C) {
+      const int ab = cc / C, c = cc - ab * C;
+      const int r = 2 * t + (ab >> 1), s2 = 2 * u + (ab & 1);
+      if (r < 7 && s2 < 7) v = w[((long long)k * 49 + r * 7 + s2) * C + c];
+    }
+    ws[i] = v;
+  }
+}
+// dw[k][r][s][c] += dWs[k][t][u][(a*2+b)*C + c],  r = 2t+a, s = 2u+b
+__global__ void s2d_unfilter_add_kernel(const float* __restrict__ dws, float* __restrict__ dw, int K, int C, int Cp) {
+  const int total = K * 49 * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, rs = (i / C) % 49, k = i / (C * 49);
+    const int r = rs / 7, s2 = rs - r * 7;
+    const int t = r >> 1, a2 = r & 1, u = s2 >> 1, b2 = s2 & 1;
+    dw[i] += dws[((long long)k * 16 + t * 4 + u) * Cp + (a2 * 2 + b2) * C + c];
+  }
+}
+
 __global__ void pad_filter_kernel(const bf16* __restrict__ w, bf16* __restrict__ wp, int K, int RSC, int Kpad) {
   const int total = K * Kpad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -743,7 +850,13 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.stride = a.stride; p.pad = a.pad; p.dil = a.dil; p.Ho = a.Ho; p.Wo = a.Wo;
   choose_brick(a.N, a.Ho, a.Wo, kTileM, 1, &p.BW, &p.BH, &p.BNI);
   p.tiles_w = (a.Wo + p.BW - 1) / p.BW; p.tiles_h = (a.Ho + p.BH - 1) / p.BH; p.tiles_n = (a.N + p.BNI - 1) / p.BNI;
-  int nk = (a.K + 255) / 256;
+  p.cblocks = (a.C + kBlockK - 1) / kBlockK;
+  // Output-channel tile: up to 256 wide for the deep (tensor-bound) layers; layers with a short
+  // contraction are store-bound.
+  static const int env_cap = getenv("B2POSE_TC_BN_CAP") ? atoi(getenv("B2POSE_TC_BN_CAP")) : 0;
+  int bn_cap = 256;            // (measured: narrower tiles only add per-tile overhead, also for the 1x1 layers)
+  if (env_cap > 0) bn_cap = env_cap;
+  int nk = (a.K + bn_cap - 1) / bn_cap;
   p.BN = (((a.K + nk - 1) / nk) + 15) / 16 * 16;
   p.tiles_k = (a.K + p.BN - 1) / p.BN;
   p.cblocks = (a.C + kBlockK - 1) / kBlockK;      // a ragged last block is zero-filled by TMA on the A side
@@ -752,10 +865,12 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   static const bool no_tma_store = getenv("B2POSE_TC_NO_TMA_STORE") != nullptr;      // tuning switches
   static const bool no_fused_stats = getenv("B2POSE_TC_NO_FUSED_STATS") != nullptr;
   p.tma_store = (p.BN % 64 == 0 && a.out_stride_sp == 1 && !no_tma_store) ? 1 : 0;
-  // fused statistics for the wide-spatial layers (K <= 512); deep layers are small and keep the separate pass
-  p.bn_sums = (p.tma_store && a.bn_sums && a.K <= 512 && !no_fused_stats) ? a.bn_sums : nullptr;
+  static const int env_debug = getenv("B2POSE_TC_DEBUG") ? atoi(getenv("B2POSE_TC_DEBUG")) : 0;
+  p.debug = env_debug;
+  // fused statistics for the wide-spatial layers (K <= 256); deeper layers are small and keep the separate pass
+  p.bn_sums = (p.tma_store && a.bn_sums && a.K <= 256 && !no_fused_stats) ? a.bn_sums : nullptr;
   if (a.stats_fused) *a.stats_fused = p.bn_sums != nullptr;
-  const int extra = (p.tma_store ? kStaging * (int)kABytes : 0) + (p.bn_sums ? 32 * a.K : 0);
+  const int extra = (p.tma_store ? kStaging * (int)kABytes : 0) + (p.bn_sums ? 64 * a.K : 0);
   int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars) - extra) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   B2_REQUIRE(stages >= 2, B2_E_UNSUPPORTED, "conv_tc: not enough shared memory for two stages");
@@ -779,7 +894,7 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   } else {
     mo = ma;
   }
-  const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024 + extra;
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024 + 16 + extra;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit());
@@ -788,7 +903,7 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   }
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_k;
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
-  conv_tc_kernel<<<grid, kThreads, smem, st>>>(ma, mb, mo, p);
+  conv_tc_kernel<<<grid, kConvThreads, smem, st>>>(ma, mb, mo, p);
   B2_LAUNCH_CHECK("conv_tc_kernel");
   return B2_OK;
 }
@@ -809,7 +924,27 @@ namespace {
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 inline bool is_stem(const B2ConvDesc* d) { return d->C <= 4 && d->R * d->S * d->C >= 32; }
+// the networks' stems: 7x7, stride 2, pad 3 -> 4x4 stride-1 convolution over the space-to-depth view
+inline bool is_s2d_stem(const B2ConvDesc* d) {
+  // (C >= 3: for one input channel the im2col matrix is only 56 columns wide and measures faster)
+  return is_stem(d) && d->C >= 3 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->dil == 1;
+}
+inline int s2d_cp(const B2ConvDesc* d) { return (4 * d->C + 7) / 8 * 8; }
+inline int s2d_h2(const B2ConvDesc* d) { return (d->H + 2) / 2; }
+inline int s2d_w2(const B2ConvDesc* d) { return (d->W + 2) / 2; }
+inline size_t s2d_view_bytes(const B2ConvDesc* d) {
+  return (size_t)d->N * s2d_h2(d) * s2d_w2(d) * s2d_cp(d) * 2;
+}
 inline int stem_kpad(const B2ConvDesc* d) { return (d->R * d->S * d->C + 7) / 8 * 8; }
+
+int launch_s2d(const B2ConvDesc* d, const void* x, const float* mask, bf16* xs, cudaStream_t st) {
+  const int cp = s2d_cp(d), h2 = s2d_h2(d), w2 = s2d_w2(d);
+  const long long total = (long long)d->N * h2 * w2 * (cp / 8);
+  long long want = (total + 255) / 256, cap = (long long)b2_num_sms() * 16;
+  s2d_kernel<<<(int)(want > cap ? cap : want), 256, 0, st>>>((const bf16*)x, mask, xs, d->N, d->H, d->W, d->C, h2, w2, cp);
+  B2_LAUNCH_CHECK("s2d");
+  return B2_OK;
+}
 
 int launch_im2col(const B2ConvDesc* d, const void* x, const float* mask, bf16* col, cudaStream_t st) {
   const int kpad = stem_kpad(d);
@@ -842,6 +977,12 @@ size_t conv_tc_workspace_bytes(const B2ConvDesc* d, int op) {
   size_t ws = 0;
   const bool partial = d->flags & B2_CONV_PARTIAL;
   const size_t dy_bytes = align256((size_t)d->N * d->Ho * d->Wo * d->K * 2);
+  if (is_s2d_stem(d)) {
+    ws += align256(s2d_view_bytes(d));                                    // space-to-depth view
+    ws += align256((size_t)d->K * 16 * s2d_cp(d) * (op == 2 ? 4 : 2));    // 4x4 filter / its gradient
+    if (op == 2 && partial && !(d->flags & B2_CONV_DY_PRESCALED)) ws += dy_bytes;
+    return ws;
+  }
   if (is_stem(d)) {
     const size_t kpad = stem_kpad(d);
     ws += align256((size_t)d->N * d->Ho * d->Wo * kpad * 2);            // im2col matrix
@@ -863,7 +1004,17 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
   a.act = x; a.N = d->N; a.H = d->H; a.W = d->W; a.C = d->C;
   a.filt = w; a.K = d->K; a.R = d->R; a.S = d->S; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
-  if (is_stem(d)) {
+  if (is_s2d_stem(d)) {
+    const int cp = s2d_cp(d);
+    bf16* xs = (bf16*)workspace;
+    bf16* wsf = (bf16*)((uint8_t*)workspace + align256(s2d_view_bytes(d)));
+    int rc = launch_s2d(d, x, (partial && !premasked) ? mask_in : nullptr, xs, st);
+    if (rc) return rc;
+    s2d_filter_kernel<<<(d->K * 16 * cp + 255) / 256, 256, 0, st>>>((const bf16*)w, wsf, d->K, d->C, cp);
+    B2_LAUNCH_CHECK("s2d_filter");
+    a.act = xs; a.H = s2d_h2(d); a.W = s2d_w2(d); a.C = cp; a.filt = wsf; a.R = 4; a.S = 4; a.stride = 1; a.pad = 1;
+    a.dil = 1;
+  } else if (is_stem(d)) {
     const int kpad = stem_kpad(d);
     bf16* col = (bf16*)workspace;
     bf16* wp = (bf16*)((uint8_t*)workspace + align256((size_t)d->N * d->Ho * d->Wo * kpad * 2));
@@ -982,7 +1133,22 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   float* dw_out = dw;
   float* dwp = nullptr;
   int kpad = 0;
-  if (is_stem(d)) {
+  bool s2d = false;
+  if (is_s2d_stem(d)) {
+    s2d = true;
+    kpad = s2d_cp(d);
+    bf16* xs = (bf16*)ws;
+    ws += align256(s2d_view_bytes(d));
+    dwp = (float*)ws;
+    ws += align256((size_t)d->K * 16 * kpad * 4);
+    int rc = launch_s2d(d, x, (partial && !premasked) ? mask_in : nullptr, xs, st);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)d->K * 16 * kpad * 4, st);
+    B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc_wgrad: memset failed: %s", cudaGetErrorString(e));
+    x = xs;
+    g.H = s2d_h2(d); g.W = s2d_w2(d); g.C = kpad; g.R = 4; g.S = 4; g.stride = 1; g.pad = 1; g.dil = 1;
+    dw_out = dwp;
+  } else if (is_stem(d)) {
     kpad = stem_kpad(d);
     bf16* col = (bf16*)ws;
     ws += align256((size_t)d->N * d->Ho * d->Wo * kpad * 2);
@@ -1025,8 +1191,13 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   p.ctiles = (d->C + p.BNc - 1) / p.BNc;
   p.ktiles = (d->K + 127) / 128;
   const int taps = d->R * d->S;
+  p.T = 256 / p.BNc;                       // 2 accumulator sets x T x BNc <= 512 TMEM columns
+  if (p.T > taps) p.T = taps;
+  if (p.T < 1) p.T = 1;
+  p.tgroups = (taps + p.T - 1) / p.T;
+  p.T = (taps + p.tgroups - 1) / p.tgroups;   // balance the groups (9 taps: 3+3+3, not 4+4+1)
   const long long bricks = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
-  const long long base_items = (long long)taps * p.ctiles * p.ktiles;
+  const long long base_items = (long long)p.tgroups * p.ctiles * p.ktiles;
   // enough pixel splits to fill the machine ~2x, but at least 8 bricks (512 pixels) per item
   long long want = (2LL * b2_num_sms() + base_items - 1) / base_items;
   long long max_splits = (bricks + 7) / 8;
@@ -1034,11 +1205,11 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   if (want < 1) want = 1;
   p.bricks_per_split = (int)((bricks + want - 1) / want);
   p.splits = (int)((bricks + p.bricks_per_split - 1) / p.bricks_per_split);
-  const int stage_bytes = 2 * kWgPix * 128 + (p.BNc / 64) * kWgPix * 128;
+  const int stage_bytes = 2 * kWgPix * 128 + p.T * (p.BNc / 64) * kWgPix * 128;
   int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  p.tmem_cols = pow2_cols(2 * p.BNc);
+  p.tmem_cols = pow2_cols(2 * p.T * p.BNc);
   p.dw = dw_out;
   CUtensorMap mdy, mx;
   int rc = make_act_map(&mdy, dys, d->N, d->Ho, d->Wo, d->K, p.BW, p.BH, p.BNI, 1);
@@ -1056,7 +1227,10 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
   wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(mdy, mx, p);
   B2_LAUNCH_CHECK("wgrad_tc_kernel");
-  if (dwp) {
+  if (dwp && s2d) {
+    s2d_unfilter_add_kernel<<<(d0->K * 49 * d0->C + 255) / 256, 256, 0, st>>>(dwp, dw, d0->K, d0->C, kpad);
+    B2_LAUNCH_CHECK("s2d_unfilter_add");
+  } else if (dwp) {
     const int rsc = d0->R * d0->S * d0->C;
     unpad_add_kernel<<<(d0->K * rsc + 255) / 256, 256, 0, st>>>(dwp, dw, d0->K, rsc, kpad);
     B2_LAUNCH_CHECK("unpad_add");

@@ -152,7 +152,7 @@ def test_graph_replay_matches_eager(b2pose, dev):
         traj[use_graph] = [float(tr.train_step(batch)["loss"]) for _ in range(6)]
         traj[(use_graph, "w")] = net.state_dict()["layer3.0.conv1.weight"].clone()
         traj[(use_graph, "nbt")] = int(net.state_dict()["bn1.num_batches_tracked"])
-    np.testing.assert_allclose(traj[True][:4], traj[False][:4], rtol=2e-4)      # 3 eager warm-ups + first replay
+    np.testing.assert_allclose(traj[True][:4], traj[False][:4], rtol=1e-3)      # 3 eager warm-ups + first replay
     np.testing.assert_allclose(traj[True], traj[False], rtol=5e-3)              # fp32 wgrad atomics reorder sums
     assert rel_err(traj[(True, "w")], traj[(False, "w")]) < 1e-3
     assert traj[(True, "nbt")] == traj[(False, "nbt")] == 6

@@ -33,6 +33,9 @@ CASES = [
     ("stem_rgb",      2, 3,    64,  64, 64, 7, 2, 3, 1, False, False, False),
     ("stem_depth_pc", 2, 1,    64,  65, 65, 7, 2, 3, 1, True,  False, False),
     ("c_tail",        2, 72,   80,  12, 12, 3, 1, 1, 1, False, False, False),
+    ("stem_rgb_odd",  2, 3,    64,  65, 65, 7, 2, 3, 1, False, False, False),
+    ("stem_c4",       1, 4,    64,  32, 32, 7, 2, 3, 1, False, False, False),
+    ("smallc_5x5",    2, 3,    32,  20, 20, 5, 1, 2, 1, False, False, False),
 ]
 
 
