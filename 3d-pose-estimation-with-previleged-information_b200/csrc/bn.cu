@@ -375,6 +375,7 @@ extern "C" int b2_bn_stats(const void* y, int64_t rows, int32_t C, int32_t dtype
   B2_REQUIRE(y && partials && rows > 0 && C > 0, B2_E_BADARG, "bn_stats: bad argument");
   B2_REQUIRE((C & 3) == 0, B2_E_UNSUPPORTED, "bn_stats: C=%d is not a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
+  if (bn_stream_eligible(C, dtype)) return bn_stream_stats(y, rows, C, partials, st);
   const int nv = vec_width(C, dtype);
   Geo g = geometry(rows, C / nv, 16, 2, true);
   size_t sh = 2 * sizeof(float) * nv * g.block.x * g.block.y;
@@ -403,6 +404,8 @@ extern "C" int b2_bn_apply(const void* y, const float* mean, const float* invstd
   B2_REQUIRE(y && z && mean && invstd && gamma && beta && rows > 0 && C > 0, B2_E_BADARG, "bn_apply: bad argument");
   B2_REQUIRE((C & 3) == 0, B2_E_UNSUPPORTED, "bn_apply: C=%d is not a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
+  if (bn_stream_eligible(C, dtype))
+    return bn_stream_apply(y, residual, z, mean, invstd, gamma, beta, row_mask, relu, rows, C, st);
   ApplyP p;
   p.mean = mean; p.invstd = invstd; p.gamma = gamma; p.beta = beta; p.row_mask = row_mask; p.relu = relu;
   p.rows = rows; p.C = C;
@@ -426,6 +429,8 @@ extern "C" int b2_bn_bwd_reduce(const void* dz, const void* z, const void* y, co
              B2_E_BADARG, "bn_bwd_reduce: bad argument");
   B2_REQUIRE((C & 3) == 0, B2_E_UNSUPPORTED, "bn_bwd_reduce: C=%d is not a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
+  if (bn_stream_eligible(C, dtype))
+    return bn_stream_bwd_reduce(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, partials, rows, C, st);
   const int nv = vec_width(C, dtype);
   Geo g = geometry(rows, C / nv, 16, 2, true);
   size_t sh = 2 * sizeof(float) * nv * g.block.x * g.block.y;
@@ -458,6 +463,9 @@ extern "C" int b2_bn_bwd_apply(const void* dz, const void* z, const void* y, con
              "bn_bwd_apply: bad argument");
   B2_REQUIRE((C & 3) == 0, B2_E_UNSUPPORTED, "bn_bwd_apply: C=%d is not a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
+  if (bn_stream_eligible(C, dtype))
+    return bn_stream_bwd_apply(dz, z, y, mean, invstd, gamma, beta, gsum, row_mask, row_scale, relu, training, dy,
+                               d_residual, rows, C, st);
   const int nv = vec_width(C, dtype);
   Geo g = geometry(rows, C / nv, 8, 4);
   if (dtype == B2_F32)

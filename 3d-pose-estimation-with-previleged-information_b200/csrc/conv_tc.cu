@@ -335,7 +335,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = valid ? __uint_as_float(v[j * 8 + e]) * scale : 0.f;
             const int chunk = half * 4 + j;
-            store8(reinterpret_cast<bf16*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)), f);
+            if (!(p.debug & 8)) store8(reinterpret_cast<bf16*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)), f);
+            else if (f[0] == 12345.678f) p.out[0] = __float2bfloat16(f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7]);
           }
         }
         tc_fence_before();                        // accumulator fully read: hand TMEM back to the MMA warp
@@ -349,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                          ni * p.BNI);
           bulk_commit();
         }
-        if (p.bn_sums) {
+        if (p.bn_sums && !(p.debug & 4)) {
           // per-channel sum / sum of squares of the staged tile: 16-byte shared loads (a quarter-warp
           // reads one whole 128-byte row), two shuffle steps, warp-private fp32 accumulators
           const int chunk = ep_tid & 7, rsub = ep_tid >> 3;        // rsub 0..31
