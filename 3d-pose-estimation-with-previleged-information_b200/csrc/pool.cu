@@ -6,6 +6,110 @@
 
 namespace {
 
+// ---- bf16, 8 channels (16 bytes) per thread -------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_fwd8_kernel(const bf16* __restrict__ x, const float* __restrict__ veil_in,
+                                                          bf16* __restrict__ y, uint8_t* __restrict__ argmax,
+                                                          float* __restrict__ veil_out, int N, int H, int W, int C,
+                                                          int Ho, int Wo) {
+  const int C8 = C >> 3;
+  const long long total = (long long)N * Ho * Wo * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    const long long pix = i / C8;
+    const int ow = (int)(pix % Wo);
+    const long long t = pix / Wo;
+    const int oh = (int)(t % Ho), n = (int)(t / Ho);
+    float v[9][8];
+    bool ok[9];
+    // issue all (up to 9) 16-byte loads first
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ih = oh * 2 - 1 + r, iw = ow * 2 - 1 + s;
+        ok[r * 3 + s] = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        if (ok[r * 3 + s]) load8(x + (((long long)n * H + ih) * W + iw) * C + cg * 8, v[r * 3 + s]);
+      }
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+    float vmax = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (!ok[k]) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v[k][j] > best[j] || v[k][j] != v[k][j]) { best[j] = v[k][j]; arg[j] = k; }
+      if (veil_in && cg == 0) {
+        const int ih = oh * 2 - 1 + k / 3, iw = ow * 2 - 1 + k % 3;
+        vmax = fmaxf(vmax, veil_in[((long long)n * H + ih) * W + iw]);
+      }
+    }
+    store8(y + pix * C + cg * 8, best);
+    if (argmax) {
+      uint2 a;
+      a.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
+      a.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
+      *reinterpret_cast<uint2*>(argmax + pix * C + cg * 8) = a;
+    }
+    if (veil_out && cg == 0) veil_out[pix] = vmax;
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd8_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ argmax,
+                                                          bf16* __restrict__ dx, int N, int H, int W, int C, int Ho,
+                                                          int Wo) {
+  const int C8 = C >> 3;
+  const long long total = (long long)N * H * W * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    const long long pix = i / C8;
+    const int iw = (int)(pix % W);
+    const long long t = pix / W;
+    const int ih = (int)(t % H), n = (int)(t / H);
+    // the (at most 2 x 2) output windows containing (ih, iw): oh in {(ih+1)/2, and (ih+1)/2 - 1 for odd ih}
+    const int oh_hi = (ih + 1) >> 1, ow_hi = (iw + 1) >> 1;
+    const int nh = (ih & 1) ? 2 : 1, nw = (iw & 1) ? 2 : 1;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    float g[4][8];
+    uint2 a[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int w2 = 0; w2 < 2; ++w2) {
+        const int oh = oh_hi - u, ow = ow_hi - w2;
+        const int k = u * 2 + w2;
+        ok[k] = u < nh && w2 < nw && oh >= 0 && oh < Ho && ow >= 0 && ow < Wo;
+        if (ok[k]) {
+          const long long op = (((long long)n * Ho + oh) * Wo + ow) * C + cg * 8;
+          load8(dy + op, g[k]);
+          a[k] = *reinterpret_cast<const uint2*>(argmax + op);
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int w2 = 0; w2 < 2; ++w2) {
+        const int k = u * 2 + w2;
+        if (!ok[k]) continue;
+        const int oh = oh_hi - u, ow = ow_hi - w2;
+        const uint32_t code = (uint32_t)((ih - (oh * 2 - 1)) * 3 + (iw - (ow * 2 - 1)));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t aj = ((j < 4 ? a[k].x : a[k].y) >> ((j & 3) * 8)) & 0xffu;
+          if (aj == code) acc[j] += g[k][j];
+        }
+      }
+    store8(dx + pix * C + cg * 8, acc);
+  }
+}
+
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, const float* __restrict__ veil_in, T* __restrict__ y,
                                    uint8_t* __restrict__ argmax, float* __restrict__ veil_out, int N, int H, int W,
@@ -87,7 +191,7 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
 }
 
 inline int pool_grid(long long total) {
-  long long want = (total + 255) / 256, cap = (long long)b2_num_sms() * 8;
+  long long want = (total + 255) / 256, cap = (long long)b2_num_sms() * 16;
   return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
@@ -104,6 +208,9 @@ extern "C" int b2_maxpool3x3s2_fwd(const void* x, const float* veil_in, void* y,
   if (dtype == B2_F32)
     maxpool_fwd_kernel<float><<<pool_grid(total), 256, 0, st>>>((const float*)x, veil_in, (float*)y, argmax, veil_out,
                                                               N, H, W, C, Ho, Wo);
+  else if ((C & 7) == 0)
+    maxpool_fwd8_kernel<<<pool_grid(total / 2), 256, 0, st>>>((const bf16*)x, veil_in, (bf16*)y, argmax, veil_out, N, H,
+                                                             W, C, Ho, Wo);
   else
     maxpool_fwd_kernel<bf16><<<pool_grid(total), 256, 0, st>>>((const bf16*)x, veil_in, (bf16*)y, argmax, veil_out, N,
                                                              H, W, C, Ho, Wo);
@@ -120,6 +227,8 @@ extern "C" int b2_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* 
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2_F32)
     maxpool_bwd_kernel<float><<<pool_grid(total), 256, 0, st>>>((const float*)dy, argmax, (float*)dx, N, H, W, C, Ho, Wo);
+  else if ((C & 7) == 0)
+    maxpool_bwd8_kernel<<<pool_grid(total / 2), 256, 0, st>>>((const bf16*)dy, argmax, (bf16*)dx, N, H, W, C, Ho, Wo);
   else
     maxpool_bwd_kernel<bf16><<<pool_grid(total), 256, 0, st>>>((const bf16*)dy, argmax, (bf16*)dx, N, H, W, C, Ho, Wo);
   B2_LAUNCH_CHECK("maxpool_bwd");

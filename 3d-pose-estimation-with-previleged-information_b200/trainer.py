@@ -154,6 +154,10 @@ class Trainer:
         self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.use_graph = use_graph
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._stage = {}
+        self._prefetched = None
+        self._stage_free = None
         self.launches_per_step = 0
         self._graphs = {}
         self._static = {}
@@ -235,13 +239,42 @@ class Trainer:
         self._hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** t)
         self.hyper.copy_(self._hyper_host, non_blocking=True)
 
-    def _static_batch(self, batch):
+    def _buffers(self, table, batch):
         key = tuple(tuple(t.shape) for t in batch)
-        st = self._static.get(key)
+        st = table.get(key)
         if st is None:
             st = tuple(torch.empty(t.shape, dtype=(torch.uint8 if t.dtype == torch.bool else t.dtype),
                                    device=self.device) for t in batch)
-            self._static[key] = st
+            table[key] = st
+        return key, st
+
+    def prefetch(self, batch):
+        """Start the host->device copy of the NEXT batch on a side stream so that it overlaps the
+        current step (the DataLoader's pinned batches; depth_train.py:386-389 does this copy inline).
+        `train_step(batch)` with the same tensors then only does a device-to-device hand-over."""
+        _, stage = self._buffers(self._stage, batch)
+        cs = self._copy_stream
+        if self._stage_free is not None:
+            cs.wait_event(self._stage_free)          # the previous hand-over has read the staging buffers
+        with torch.cuda.stream(cs):
+            for s, t in zip(stage, batch):
+                s.copy_(t.view(torch.uint8) if t.dtype == torch.bool else t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._prefetched = (tuple(id(t) for t in batch), ev, stage)
+
+    def _static_batch(self, batch):
+        key, st = self._buffers(self._static, batch)
+        pf = self._prefetched
+        if pf is not None and pf[0] == tuple(id(t) for t in batch):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(pf[1])
+            for s, g in zip(st, pf[2]):
+                s.copy_(g, non_blocking=True)
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(cur)
+            self._prefetched = None
+            return key, st
         for s, t in zip(st, batch):
             s.copy_(t.view(torch.uint8) if t.dtype == torch.bool else t, non_blocking=True)
         return key, st
@@ -305,8 +338,16 @@ class Trainer:
     def _epoch(self, epoch, data_loader, device):
         n_batches = len(data_loader)
         loss_avg, total = 0.0, 0
-        for i_batch, batch in enumerate(data_loader):
-            out = self.train_step(tuple(batch))
+        it = iter(data_loader)
+        nxt = next(it, None)
+        i_batch = -1
+        while nxt is not None:
+            batch, i_batch = tuple(nxt), i_batch + 1
+            out = self.train_step(batch)
+            nxt = next(it, None)
+            if nxt is not None and not nxt[0].is_cuda:
+                nxt = tuple(nxt)
+                self.prefetch(nxt)                  # overlaps this step's compute
             n = batch[2].size(0)
             val = out["loss"].item()
             print("| train Epoch[%d] [%d/%d]  Loss %1.4f" % (epoch, i_batch, n_batches, val), flush=True)

@@ -126,3 +126,24 @@ def test_adam_clip(b2pose, dev):
     L.call("b2_adam_step", L.ptr(w), L.ptr(gd), L.ptr(m), L.ptr(v), None, n, 5e-5, 0.9, 0.999, 1e-8, 4e-5, 4,
            L.ptr(ss), 5.0, 1.0, None, L.stream())
     assert torch.equal(w, before)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16), (1, 64, 17, 13), (3, 8, 9, 9), (2, 12, 6, 7)])
+def test_maxpool_with_veil(b2pose, dev, shape, dtype):
+    """MaxPool2d(3,2,1) on x and the veil in one launch (partial_depthnet.py:219-220), fwd + bwd."""
+    N, C, H, W = shape
+    gen = torch.Generator().manual_seed(N * 1000 + C + H)
+    x = torch.randn(N, C, H, W, generator=gen).to(dtype).float()
+    veil = (torch.rand(N, 1, H, W, generator=gen) > 0.6).float()
+    xr = x.clone().requires_grad_(True)
+    yr = torch.nn.functional.max_pool2d(xr, 3, 2, 1)
+    vr = torch.nn.functional.max_pool2d(veil, 3, 2, 1)
+    cot = torch.randn(yr.shape, generator=gen).to(dtype).float()
+    (yr * cot).sum().backward()
+    xg = x.permute(0, 2, 3, 1).contiguous().to(dev).to(dtype).requires_grad_(True)
+    yg, vg = b2pose.ops.MaxPoolFn.apply(xg, veil[:, 0].contiguous().to(dev))
+    (yg.float() * cot.permute(0, 2, 3, 1).to(dev)).sum().backward()
+    assert torch.equal(yg.float().cpu().permute(0, 3, 1, 2), yr.detach())        # selection: exact
+    assert torch.equal(vg.cpu(), vr[:, 0])
+    assert rel_err(xg.grad.float().permute(0, 3, 1, 2), xr.grad) < (1e-6 if dtype == torch.float32 else 1e-2)

@@ -200,3 +200,25 @@ def test_state_dict_and_api(b2pose, dev):
     net2 = b2pose.partial_fusionnet.resnet50(cfg, False)
     net2.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
     assert torch.equal(net2.layer6[0].conv2.weight, net.layer6[0].conv2.weight.cpu())
+
+
+def test_epoch_loop_prefetch(b2pose, dev):
+    """Trainer.train(epoch, loader) with pinned host batches (one-batch lookahead H2D on a side
+    stream) follows the same trajectory as feeding device batches step by step."""
+    kind, model = "partial_depthnet", "resnet18"
+    cfg = po.net_config(side_in=64, num_joints=17)
+    batches = [po.synth_batch(2, 64, 17, seed=10 + i) for i in range(4)]
+    out = {}
+    for mode in ("steps", "epoch"):
+        net = build(b2pose, dev, kind, model, cfg)
+        net.train()
+        tr = b2pose.Trainer(targs(b2pose, kind, model, cfg), net, dict(key_index=16), use_graph=False)
+        if mode == "steps":
+            tr.adapt_learn_rate(1)
+            losses = [float(tr.train_step(tuple(t.to(dev) for t in b))["loss"]) for b in batches]
+            out[mode] = sum(l * 2 for l in losses) / 8
+        else:
+            pinned = [tuple(t.pin_memory() for t in b) for b in batches]
+            out[mode] = tr.train(1, pinned)["cam_train_loss"]
+            assert tr.lr == pytest.approx(5e-5 * 0.2)            # warm-up epoch (depth_train.py:621-625)
+    assert out["epoch"] == pytest.approx(out["steps"], rel=2e-3)
