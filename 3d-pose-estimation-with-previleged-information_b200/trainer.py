@@ -151,7 +151,7 @@ class Trainer:
         self.step_count = 0
         self.betas, self.eps = (0.9, 0.999), 1e-8
         self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self._hyper_ring = [(torch.zeros(4, dtype=torch.float32).pin_memory(), None) for _ in range(8)]
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.use_graph = use_graph
         self._copy_stream = torch.cuda.Stream(device=dev)
@@ -234,10 +234,17 @@ class Trainer:
     def _set_hyper(self):
         self.step_count += 1
         t = self.step_count
-        self._hyper_host[0] = self.lr
-        self._hyper_host[1] = 1.0 - self.betas[0] ** t
-        self._hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** t)
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        slot = t % len(self._hyper_ring)
+        host, ev = self._hyper_ring[slot]
+        if ev is not None:
+            ev.synchronize()                         # the async copy that last read this pinned slot is done
+        host[0] = self.lr
+        host[1] = 1.0 - self.betas[0] ** t
+        host[2] = math.sqrt(1.0 - self.betas[1] ** t)
+        self.hyper.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_ring[slot] = (host, ev)
 
     def _buffers(self, table, batch):
         key = tuple(tuple(t.shape) for t in batch)
@@ -252,8 +259,13 @@ class Trainer:
         """Start the host->device copy of the NEXT batch on a side stream so that it overlaps the
         current step (the DataLoader's pinned batches; depth_train.py:386-389 does this copy inline).
         `train_step(batch)` with the same tensors then only does a device-to-device hand-over."""
+        fresh = tuple(tuple(t.shape) for t in batch) not in self._stage
         _, stage = self._buffers(self._stage, batch)
         cs = self._copy_stream
+        if fresh:
+            # the staging buffers may recycle memory whose last users are still queued on the compute
+            # stream; order the first side-stream write after them
+            cs.wait_stream(torch.cuda.current_stream())
         if self._stage_free is not None:
             cs.wait_event(self._stage_free)          # the previous hand-over has read the staging buffers
         with torch.cuda.stream(cs):

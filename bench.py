@@ -275,12 +275,16 @@ def run_b200(args):
         out = trainer.train_step(resident)
     barrier()
 
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    losses = []
+
     def timed(batch, read_back):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.perf_counter()
         e0.record()
         last = None
+        pending = None
         if read_back:
             trainer.prefetch(batch)                 # H2D of step 0 (inside the timed region)
         for i in range(args.steps):
@@ -288,7 +292,18 @@ def run_b200(args):
             if read_back:
                 if i + 1 < args.steps:
                     trainer.prefetch(batch)         # H2D of step i+1 overlaps the compute of step i
-                last["loss"].item()
+                # D2H of this step's loss into pinned memory; it is consumed one step later so the
+                # host never stalls the launch of the next step
+                loss_host[i % 2].copy_(last["loss"], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[0].synchronize()
+                    losses.append(float(loss_host[pending[1]]))
+                pending = (ev, i % 2)
+        if pending is not None:
+            pending[0].synchronize()
+            losses.append(float(loss_host[pending[1]]))
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
@@ -320,7 +335,7 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, out2 = timed(host, True)
-    loss = float(out2["loss"])
+    loss = losses[-1] if losses else float(out2["loss"])
     if not (loss == loss):
         raise RuntimeError("bench: loss is NaN")
 
