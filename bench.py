@@ -129,6 +129,13 @@ def cpu_step_rate(args, steps, warmup, batch):
     return batch * steps / dt, cores, sample, dt / steps * 1e3
 
 
+def workload_config(args, world):
+    wl = WORKLOADS[args.workload]
+    return {"workload": "%s, %s, batch %d/GPU, %dx%d, J=%d, D=16, stride 16, fwd+head+loss+bwd+clip+Adam"
+                        % (wl["desc"], args.model, args.batch, args.side, args.side, args.joints),
+            "parallelism": "dp%d" % world}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -142,8 +149,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s %s %dx%d J=%d, CPU sample batch %d" % (wl["kind"], args.model, args.side,
-                                                                         args.side, args.joints, args.cpu_batch)},
+        "config": dict(workload_config(args, args.gpus), sample="CPU (oracle port of the reference step, fp32, all host "
+                       "threads): each step = one batch of %d of the same workload" % args.cpu_batch),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -346,10 +353,8 @@ def run_b200(args):
         "metric": METRIC, "value": total / ms_dev * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "%s, %s, batch %d/GPU, %dx%d, J=%d, D=16, stride 16, fwd+head+loss+bwd+clip+Adam"
-                               % (wl["desc"], args.model, args.batch, args.side, args.side, args.joints),
-                   "parallelism": "dp%d" % world, "cuda_graph": trainer.use_graph,
-                   "l2": "per-step working set (activations, several GB) far exceeds the 126 MB L2; no flush needed"},
+        "config": dict(workload_config(args, world), cuda_graph=trainer.use_graph,
+                       l2="per-step working set (activations, several GB) far exceeds the 126 MB L2; no flush needed"),
         "e2e": {"value": total / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(per_step) * args.steps,
@@ -375,7 +380,14 @@ def run_b200(args):
         else:
             peak = peaks.get("hbm_gbs", 6650.0)
             roof = dict(bound="hbm", achieved=top["gbs"], peak=peak, unit="GB/s", frac=top["gbs"] / peak)
-        roof.update(traffic=None, kernel="conv_%s %s" % (top["op"], top["shape"]), launch_ms=top["ms"],
+        kname = "conv_%s %s" % (top["op"], top["shape"])
+        traffic = None
+        try:                         # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname, {}).get("dram_bytes")
+        except (OSError, ValueError):
+            pass
+        roof.update(traffic=traffic, kernel=kname, launch_ms=top["ms"], algorithmic_bytes=top["bytes"],
+                    algorithmic_flops=top["flops"],
                     tensor_cores=top["tc"], peak_source="MEASURED_PEAKS.json (burst)" if peaks else "fallback",
                     share_of_conv_time=top["total_ms"] / max(sum(r["total_ms"] for r in rows), 1e-9))
         line["roofline"] = roof
