@@ -91,11 +91,24 @@ def check(rc, what=""):
         raise RuntimeError("libb2pose %s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 
+_SYNC_DEBUG = os.environ.get("B2POSE_SYNC") == "1"     # debugging aid: localise asynchronous faults
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise on a non-zero status."""
     global launches
     launches += 1
     check(getattr(lib(), name)(*args), name)
+    if _SYNC_DEBUG:
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:      # noqa: BLE001
+            desc = ""
+            for a in args:
+                d = getattr(a, "_obj", None)
+                if isinstance(d, ConvDesc):
+                    desc = " desc=" + str({f: getattr(d, f) for f, _ in ConvDesc._fields_})
+            raise RuntimeError("libb2pose %s faulted%s: %s" % (name, desc, e)) from e
 
 
 def ptr(t):

@@ -36,14 +36,21 @@ def bn_partials(C, device):
 
 
 def workspace(nbytes, device):
-    """Grow-only scratch buffer per (device, stream)."""
+    """Grow-only scratch buffer per device, shared by all calls (the kernels that use it run on one
+    stream, in order).  It is deliberately NOT keyed by stream: under CUDA-graph capture the current
+    stream is the capture stream, and a buffer first allocated there would live in that graph's private
+    memory pool -- a second graph (another Trainer in the same process) reusing it after the first
+    graph was destroyed faulted.  The Trainer's eager warm-up steps grow it to its final size before
+    any capture."""
     if nbytes == 0:
         return None, 0
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
-    ws = _workspaces.get(key)
+    ws = _workspaces.get(device.index)
     if ws is None or ws.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("libb2pose workspace would have to grow during CUDA-graph capture; run the "
+                               "same shapes eagerly once before capturing")
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+        _workspaces[device.index] = ws
     return ws, ws.numel()
 
 
