@@ -222,3 +222,45 @@ def test_epoch_loop_prefetch(b2pose, dev):
             out[mode] = tr.train(1, pinned)["cam_train_loss"]
             assert tr.lr == pytest.approx(5e-5 * 0.2)            # warm-up epoch (depth_train.py:621-625)
     assert out["epoch"] == pytest.approx(out["steps"], rel=2e-3)
+
+
+def test_frozen_batchnorm_and_eval(b2pose, dev):
+    """depthnet.freeze_batchnorm() (depthnet.py:158-161): BN layers run on their running statistics
+    while the rest of the net trains; gradients follow the frozen-statistics formula."""
+    kind, model = "depthnet", "resnet18"
+    cfg = po.net_config(side_in=64, num_joints=17)
+    sd = po.init_state(kind, model, cfg, seed=31)
+    g = torch.Generator().manual_seed(5)
+    for k in sd:                                     # non-trivial running statistics
+        if k.endswith("running_mean"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+    batch = po.synth_batch(2, 64, 17, seed=6)
+    ref = {k: v.clone() for k, v in sd.items()}
+    for k in po.trainable_names(ref):
+        ref[k].requires_grad_(True)
+    z, _ = po.net_forward(ref, kind, model, cfg, batch[1], None, training=False)
+    loss, spec = po.pose_loss(z, batch[2], batch[3], depth=16, num_joints=17, side_out=4, depth_range=1000.0,
+                              key_index=16)
+    loss.backward()
+    net = b2pose.depthnet.resnet18(cfg, False)
+    net.load_state_dict(sd)
+    net = net.to(dev).train()
+    net.freeze_batchnorm()
+    zg, _ = net(batch[1].to(dev))
+    coords = b2pose.heatmap_coords(zg, 16, 17, 1000.0)
+    lg, sg = b2pose.pose_loss(coords, batch[2].to(dev), batch[3].to(dev), 16)
+    lg.backward()
+    assert abs(float(lg) - float(loss)) / float(loss) < 1e-4
+    assert float((sg.cpu() - spec.detach()).abs().max()) < 0.1
+    for name in ("conv1.weight", "layer2.0.conv1.weight", "layer3.1.bn2.weight", "layer4.0.downsample.1.bias",
+                 "regressor.weight"):
+        got = dict(net.named_parameters())[name].grad
+        assert rel_err(got, ref[name].grad) < 2e-3, name
+    assert torch.equal(net.bn1.running_mean.cpu(), sd["bn1.running_mean"])      # untouched
+    assert int(net.bn1.num_batches_tracked) == 0
+    # Trainer.predict: eval-mode forward + head
+    tr = b2pose.Trainer(targs(b2pose, kind, model, cfg), net, dict(key_index=16), use_graph=False)
+    spec_eval, _ = tr.predict(batch)
+    assert float((spec_eval.cpu() - spec.detach()).abs().max()) < 0.1
