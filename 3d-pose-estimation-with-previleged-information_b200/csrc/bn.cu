@@ -160,6 +160,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, long long
                                    float eps, int training, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out) {
   __shared__ double sm[2][8][33];
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * 32 + threadIdx.x;
   float mean = 0.f, invstd = 0.f;
   if (training) {
@@ -189,6 +191,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, long long
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int C, float* __restrict__ gsum,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ double sm[2][8][33];
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s, q;
   slot_sums(partials, C, c, &s, &q, sm);
@@ -391,9 +395,8 @@ extern "C" int b2_bn_finalize(const float* partials, int64_t rows, int32_t C, fl
   B2_REQUIRE(mean && invstd && rows > 0 && C > 0, B2_E_BADARG, "bn_finalize: bad argument");
   B2_REQUIRE(training ? (partials != nullptr) : (running_mean && running_var), B2_E_BADARG,
              "bn_finalize: statistics source missing");
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(partials, rows, C, running_mean,
-                                                                              running_var, momentum, eps, training,
-                                                                              mean, invstd);
+  launch_pdl(bn_finalize_kernel, dim3((C + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream, partials,
+             (long long)rows, (int)C, running_mean, running_var, momentum, eps, (int)training, mean, invstd);
   B2_LAUNCH_CHECK("bn_finalize");
   return B2_OK;
 }
@@ -450,7 +453,8 @@ extern "C" int b2_bn_bwd_reduce(const void* dz, const void* z, const void* y, co
 extern "C" int b2_bn_bwd_finalize(const float* partials, int32_t C, float* gsum, float* dgamma, float* dbeta,
                                   void* stream) {
   B2_REQUIRE(partials && gsum && C > 0, B2_E_BADARG, "bn_bwd_finalize: bad argument");
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(partials, C, gsum, dgamma, dbeta);
+  launch_pdl(bn_bwd_finalize_kernel, dim3((C + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream, partials, (int)C, gsum,
+             dgamma, dbeta);
   B2_LAUNCH_CHECK("bn_bwd_finalize");
   return B2_OK;
 }

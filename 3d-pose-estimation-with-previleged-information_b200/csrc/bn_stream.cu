@@ -81,6 +81,7 @@ __device__ __forceinline__ void ring_setup(Ring<NIN>& r, uint8_t* smem, long lon
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();            // only shared memory was touched so far
 }
 
 // block-level reduction of per-thread partials (8 channels x 2 quantities) that share a channel
@@ -110,6 +111,7 @@ __device__ __forceinline__ void slot_reduce(const float* s, const float* q, floa
 // ---------------------------------------------------------------- stats
 __global__ void __launch_bounds__(kThreadsS, 3)
 stats_stream_kernel(const bf16* __restrict__ y, long long total_elems, int C, float* __restrict__ partials) {
+  pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   Ring<1> ring;
   ring.src[0] = reinterpret_cast<const uint8_t*>(y);
@@ -154,8 +156,10 @@ apply_stream_kernel(const bf16* __restrict__ y, const bf16* __restrict__ residua
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ row_mask, int relu,
                     long long total_elems, int C) {
+  pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   const int CV = C >> 3, cv = threadIdx.x % CV, logC = 31 - __clz(C);
+  pdl_wait();            // the per-channel constants below come from the preceding finalize kernel
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -226,6 +230,7 @@ struct BwdArgs {
 // MODE 0: reduce (partials of g and g*xhat);  MODE 1: apply (dy, d_residual)
 template <int MODE, bool HASZ>
 __global__ void __launch_bounds__(kThreadsS, 3) bwd_stream_kernel(const BwdArgs a) {
+  pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NIN = HASZ ? 3 : 2;
   Ring<NIN> ring;
@@ -355,7 +360,8 @@ int bn_stream_stats(const void* y, int64_t rows, int C, float* partials, cudaStr
   const size_t sh = smem_bytes(1, true);
   int rc = opt_in(stats_stream_kernel, sh);
   if (rc) return rc;
-  stats_stream_kernel<<<stream_grid(rows * C, 2, true), kThreadsS, sh, st>>>((const bf16*)y, rows * C, C, partials);
+  launch_pdl(stats_stream_kernel, dim3(stream_grid(rows * C, 2, true)), dim3(kThreadsS), sh, st, (const bf16*)y,
+             (long long)(rows * C), C, partials);
   B2_LAUNCH_CHECK("bn_stats(stream)");
   return B2_OK;
 }
@@ -366,8 +372,8 @@ int bn_stream_apply(const void* y, const void* residual, void* z, const float* m
   const size_t sh = smem_bytes(residual ? 2 : 1, false);
   int rc = opt_in(apply_stream_kernel, sh);
   if (rc) return rc;
-  apply_stream_kernel<<<stream_grid(rows * C, 3, false), kThreadsS, sh, st>>>(
-      (const bf16*)y, (const bf16*)residual, (bf16*)z, mean, invstd, gamma, beta, row_mask, relu, rows * C, C);
+  launch_pdl(apply_stream_kernel, dim3(stream_grid(rows * C, 3, false)), dim3(kThreadsS), sh, st, (const bf16*)y,
+             (const bf16*)residual, (bf16*)z, mean, invstd, gamma, beta, row_mask, relu, (long long)(rows * C), C);
   B2_LAUNCH_CHECK("bn_apply(stream)");
   return B2_OK;
 }
@@ -392,10 +398,10 @@ int bn_stream_bwd_reduce(const void* dz, const void* z, const void* y, const flo
   int rc;
   if (hasz) {
     if ((rc = opt_in(bwd_stream_kernel<0, true>, sh))) return rc;
-    bwd_stream_kernel<0, true><<<grid, kThreadsS, sh, st>>>(a);
+    launch_pdl(bwd_stream_kernel<0, true>, dim3(grid), dim3(kThreadsS), sh, st, a);
   } else {
     if ((rc = opt_in(bwd_stream_kernel<0, false>, sh))) return rc;
-    bwd_stream_kernel<0, false><<<grid, kThreadsS, sh, st>>>(a);
+    launch_pdl(bwd_stream_kernel<0, false>, dim3(grid), dim3(kThreadsS), sh, st, a);
   }
   B2_LAUNCH_CHECK("bn_bwd_reduce(stream)");
   return B2_OK;
@@ -413,10 +419,10 @@ int bn_stream_bwd_apply(const void* dz, const void* z, const void* y, const floa
   int rc;
   if (hasz) {
     if ((rc = opt_in(bwd_stream_kernel<1, true>, sh))) return rc;
-    bwd_stream_kernel<1, true><<<grid, kThreadsS, sh, st>>>(a);
+    launch_pdl(bwd_stream_kernel<1, true>, dim3(grid), dim3(kThreadsS), sh, st, a);
   } else {
     if ((rc = opt_in(bwd_stream_kernel<1, false>, sh))) return rc;
-    bwd_stream_kernel<1, false><<<grid, kThreadsS, sh, st>>>(a);
+    launch_pdl(bwd_stream_kernel<1, false>, dim3(grid), dim3(kThreadsS), sh, st, a);
   }
   B2_LAUNCH_CHECK("bn_bwd_apply(stream)");
   return B2_OK;

@@ -166,6 +166,7 @@ struct __align__(8) PipeBars {
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const FpropParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -195,6 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -461,6 +463,7 @@ constexpr int kWgPix = 64;         // pixels per stage
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                 const WgradParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // stage: A = dy [2 atoms of 64 k][64 pix][128 B]  (16 KB), B = T x ( x [BNc/64 atoms][64 pix][128 B] )
@@ -486,6 +489,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
 
   // item decode: split fastest so CTAs running together share the same filter tile / spread pixels
   auto decode = [&](int item, int& sp, int& tg, int& ct, int& kt) {
@@ -611,6 +615,8 @@ struct TapMap {
 __global__ void tap_transpose_kernel(const bf16* __restrict__ w, bf16* __restrict__ wt, int K, int C, int taps_src,
                                      TapMap tm) {
   __shared__ bf16 tile[32][33];
+  pdl_trigger();
+  pdl_wait();
   const int tdst = blockIdx.z, tsrc = tm.src[tdst];
   const int k0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -904,7 +910,8 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   }
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_k;
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
-  conv_tc_kernel<<<grid, kConvThreads, smem, st>>>(ma, mb, mo, p);
+  cudaError_t le = launch_pdl(conv_tc_kernel, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, mo, p);
+  B2_REQUIRE(le == cudaSuccess, B2_E_LAUNCH, "conv_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   B2_LAUNCH_CHECK("conv_tc_kernel");
   return B2_OK;
 }
@@ -1065,7 +1072,7 @@ int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const
     for (int r = 0; r < d->R; ++r)
       for (int s2 = 0; s2 < d->S; ++s2) tm.src[r * d->S + s2] = (d->R - 1 - r) * d->S + (d->S - 1 - s2);
     dim3 tg((d->C + 31) / 32, (d->K + 31) / 32, taps);
-    tap_transpose_kernel<<<tg, tb, 0, st>>>((const bf16*)w, wt, d->K, d->C, taps, tm);
+    launch_pdl(tap_transpose_kernel, tg, tb, 0, st, (const bf16*)w, wt, d->K, d->C, taps, tm);
     B2_LAUNCH_CHECK("tap_transpose");
     a.filt = wt; a.R = d->R; a.S = d->S; a.dil = d->dil; a.pad = d->dil * (d->R - 1) - d->pad;
     a.Ho = d->H; a.Wo = d->W; a.out_stride_sp = 1;
@@ -1102,7 +1109,7 @@ int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const
       for (int i = 0; i < nr; ++i)
         for (int j = 0; j < ns; ++j) tm.src[i * ns + j] = rl[i] * d->S + sl[j];
       dim3 tg((d->C + 31) / 32, (d->K + 31) / 32, tm.n);
-      tap_transpose_kernel<<<tg, tb, 0, st>>>((const bf16*)w, wcls, d->K, d->C, taps, tm);
+      launch_pdl(tap_transpose_kernel, tg, tb, 0, st, (const bf16*)w, wcls, d->K, d->C, taps, tm);
       B2_LAUNCH_CHECK("tap_transpose");
       // floor division of (ph + pad - r_max) by the stride (exact by construction)
       auto fdiv = [](int a_, int b_) { return (a_ >= 0) ? a_ / b_ : -((-a_ + b_ - 1) / b_); };
@@ -1226,7 +1233,8 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   }
   const long long total = base_items * p.splits;
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
-  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(mdy, mx, p);
+  cudaError_t le = launch_pdl(wgrad_tc_kernel, dim3(grid), dim3(kThreads), smem, st, mdy, mx, p);
+  B2_REQUIRE(le == cudaSuccess, B2_E_LAUNCH, "wgrad_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   B2_LAUNCH_CHECK("wgrad_tc_kernel");
   if (dwp && s2d) {
     s2d_unfilter_add_kernel<<<(d0->K * 49 * d0->C + 255) / 256, 256, 0, st>>>(dwp, dw, d0->K, d0->C, kpad);
