@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2pose.so")
 
 F32, BF16 = 0, 1
-CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA = 1, 2, 4, 8
+CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA, CONV_DX_ACCUMULATE = 1, 2, 4, 8, 16
 ABI_VERSION = 2
 BN_PARTS = 320
 

@@ -77,6 +77,8 @@ extern "C" int b2_pconv_dgrad(const B2ConvDesc* d, const void* dy, const float* 
     B2_REQUIRE(ws_bytes >= conv_tc_workspace_bytes(d, 1), B2_E_WORKSPACE, "pconv_dgrad: workspace too small");
     return conv_tc_dgrad(d, dy, ratio, w, mask_in, dx, workspace, st);
   }
+  B2_REQUIRE(!(d->flags & B2_CONV_DX_ACCUMULATE), B2_E_UNSUPPORTED,
+             "pconv_dgrad: B2_CONV_DX_ACCUMULATE needs the bf16 tensor-core path (stride 1, C %% 64 == 0)");
   return conv_ffma_dgrad(d, dy, ratio, w, mask_in, dx, st);
 }
 

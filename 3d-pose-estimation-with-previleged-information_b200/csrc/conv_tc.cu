@@ -85,6 +85,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -154,6 +159,7 @@ struct FpropParams {
   int out_stride_sp, out_off_h, out_off_w;             // strided dgrad: row (oh, ow) is stored at (oh*sp+off_h, ow*sp+off_w)
   int out_H, out_W;                                    // spatial size of the tensor written
   int tma_store;                                       // epilogue: smem-staged TMA store (+ fused BN statistics)
+  int accumulate;                                      // TMA reduce-add into the output instead of a plain store
   int debug;                                           // tuning experiments (B2POSE_TC_DEBUG): 1 skip epilogue, 2 skip store, 4 skip B reload
   float* bn_sums;                                      // partials[B2_BN_PARTS][2*K]: sum / sum of squares of the stored output
 };
@@ -347,9 +353,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         fence_async_smem();
         epi_barrier();
         if (ep_tid == 0 && !(p.debug & 2)) {
-          for (int g = 0; g < groups; ++g)
-            tma_store_4d(&map_out, smem_u32(sset + (size_t)g * kABytes), kbase + g * 64, wi * p.BW, hi * p.BH,
-                         ni * p.BNI);
+          for (int g = 0; g < groups; ++g) {
+            if (p.accumulate)
+              tma_reduce_add_4d(&map_out, smem_u32(sset + (size_t)g * kABytes), kbase + g * 64, wi * p.BW, hi * p.BH,
+                                ni * p.BNI);
+            else
+              tma_store_4d(&map_out, smem_u32(sset + (size_t)g * kABytes), kbase + g * 64, wi * p.BW, hi * p.BH,
+                           ni * p.BNI);
+          }
           bulk_commit();
         }
         if (p.bn_sums && !(p.debug & 4)) {
@@ -845,6 +856,7 @@ struct RunArgs {
   const void* filt; int K, R, S, stride, pad, dil, Ho, Wo;    // filt: [K][R*S*C] bf16
   void* out; int out_H, out_W, out_stride_sp, out_off_h, out_off_w;
   int pad_w, use_pad_w;                                        // pad_w is read only when use_pad_w != 0
+  int accumulate;                                              // dgrad: reduce-add into `out`
   float* bn_sums; bool* stats_fused;                          // optional fused BatchNorm statistics
   int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
   float* mask_out; float* ratio_out;
@@ -874,6 +886,9 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.tma_store = (p.BN % 64 == 0 && a.out_stride_sp == 1 && !no_tma_store) ? 1 : 0;
   static const int env_debug = getenv("B2POSE_TC_DEBUG") ? atoi(getenv("B2POSE_TC_DEBUG")) : 0;
   p.debug = env_debug;
+  p.accumulate = a.accumulate;
+  B2_REQUIRE(!a.accumulate || p.tma_store, B2_E_UNSUPPORTED,
+             "conv_tc: accumulate needs the TMA-store epilogue (output channels %% 64 == 0, stride 1)");
   // fused statistics for the wide-spatial layers (K <= 256); deeper layers are small and keep the separate pass
   p.bn_sums = (p.tma_store && a.bn_sums && a.K <= 256 && !no_fused_stats) ? a.bn_sums : nullptr;
   if (a.stats_fused) *a.stats_fused = p.bn_sums != nullptr;
@@ -977,6 +992,7 @@ bool conv_tc_supported(const B2ConvDesc* d, int op) {
   if (partial && !one && !premasked) return false;          // needs x*mask in the loader: CUDA-core path
   if (partial && one && d->stride != 1) return false;
   if (op == 0) return true;
+  if (op == 1 && (d->flags & B2_CONV_DX_ACCUMULATE)) return d->stride == 1 && d->C % 64 == 0 && d->C <= 256 * 8;
   if (op == 1) return d->stride == 1 || d->dil == 1;        // strided: one launch per output parity class
   return op == 2;
 }
@@ -1076,6 +1092,7 @@ int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const
     B2_LAUNCH_CHECK("tap_transpose");
     a.filt = wt; a.R = d->R; a.S = d->S; a.dil = d->dil; a.pad = d->dil * (d->R - 1) - d->pad;
     a.Ho = d->H; a.Wo = d->W; a.out_stride_sp = 1;
+    a.accumulate = (d->flags & B2_CONV_DX_ACCUMULATE) ? 1 : 0;
     return run_conv_tc(a, st);
   }
   // strided (dil == 1): output pixels of parity class (ph, pw) = (ih % stride, iw % stride) only see the taps

@@ -110,7 +110,8 @@ class BatchNorm2d(nn.BatchNorm2d):
         raise NotImplementedError("b2pose BatchNorm2d is evaluated fused with its convolution (conv_bn)")
 
 
-def conv_bn(x, veil, conv, bn, relu, residual=None, mask_output=False, premasked=False):
+def conv_bn(x, veil, conv, bn, relu, residual=None, mask_output=False, premasked=False, dx_holder=None,
+            res_holder=None):
     """conv -> bn (+residual) (+relu) (*veil) on NHWC tensors; returns (z, veil_out)."""
     partial = isinstance(conv, PartialConv)
     training = bn.training
@@ -120,6 +121,6 @@ def conv_bn(x, veil, conv, bn, relu, residual=None, mask_output=False, premasked
     if conv._grad_sink is not None and bn._grad_sinks is not None and torch.is_grad_enabled():
         sinks = (conv._grad_sink,) + bn._grad_sinks
     z, vout = ops.ConvBNFn.apply(x, veil if partial else None, conv.weight, conv.shadow(x.dtype), bn.weight,
-                                 bn.bias, bn.running_mean, bn.running_var, residual, cfg, sinks)
+                                 bn.bias, bn.running_mean, bn.running_var, residual, cfg, sinks, dx_holder, res_holder)
     bn.tick()
     return z, (vout if partial else veil)

@@ -38,6 +38,11 @@ class _Block(nn.Module):
         self.partial = partial
         self.skip_relu = skip_relu
 
+    def _holder(self, x):
+        """Shared dict that lets the block's first conv+BN node absorb the identity shortcut's gradient
+        (see ops.ConvBNFn); only when the shortcut is the block input itself."""
+        return {} if (self.downsample is None and torch.is_grad_enabled() and x.requires_grad) else None
+
     def _residual(self, x):
         if self.downsample is None:
             return x
@@ -60,9 +65,10 @@ class BasicBlock(_Block):
         self.stride = stride
 
     def forward_nhwc(self, x, veil):
-        res = self._residual(x)
-        out, veil = conv_bn(x, veil, self.conv1, self.bn1, relu=True, mask_output=True)
-        out, veil = conv_bn(out, veil, self.conv2, self.bn2, relu=not self.skip_relu, residual=res, premasked=True)
+        res, h = self._residual(x), self._holder(x)
+        out, veil = conv_bn(x, veil, self.conv1, self.bn1, relu=True, mask_output=True, dx_holder=h)
+        out, veil = conv_bn(out, veil, self.conv2, self.bn2, relu=not self.skip_relu, residual=res, premasked=True,
+                            res_holder=h)
         return out, veil
 
 
@@ -83,10 +89,11 @@ class Bottleneck(_Block):
         self.stride = stride
 
     def forward_nhwc(self, x, veil):
-        res = self._residual(x)
-        out, veil = conv_bn(x, veil, self.conv1, self.bn1, relu=True, mask_output=True)
+        res, h = self._residual(x), self._holder(x)
+        out, veil = conv_bn(x, veil, self.conv1, self.bn1, relu=True, mask_output=True, dx_holder=h)
         out, veil = conv_bn(out, veil, self.conv2, self.bn2, relu=True, mask_output=True, premasked=True)
-        out, veil = conv_bn(out, veil, self.conv3, self.bn3, relu=not self.skip_relu, residual=res, premasked=True)
+        out, veil = conv_bn(out, veil, self.conv3, self.bn3, relu=not self.skip_relu, residual=res, premasked=True,
+                            res_holder=h)
         return out, veil
 
 

@@ -112,13 +112,29 @@ def _conv_fprop(desc, x, mask, wk, bias, want_ratio, want_stats):
     return y, mask_out, ratio, sums
 
 
-def _conv_dgrad(desc, dy, ratio, wk, mask):
+def _conv_dgrad(desc, dy, ratio, wk, mask, addend=None):
+    """dx = dgrad(...) (+ addend).  When the tensor-core kernel can reduce-add into an existing
+    tensor, `addend` (the gradient of a residual branch) is accumulated in place and returned;
+    otherwise the sum is formed by a separate add."""
     dev = dy.device
+    if addend is not None:
+        desc.flags |= L.CONV_DX_ACCUMULATE
+        fused = bool(L.lib().b2_conv_uses_tensor_cores(C.byref(desc), 1)) and addend.is_contiguous() \
+            and addend.dtype == dy.dtype
+        if fused:
+            try:
+                ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 1), dev)
+                L.call("b2_pconv_dgrad", C.byref(desc), L.ptr(dy), L.ptr(ratio), L.ptr(wk), L.ptr(mask),
+                       L.ptr(addend), L.ptr(ws), wsn, L.stream())
+            finally:
+                desc.flags &= ~L.CONV_DX_ACCUMULATE
+            return addend
+        desc.flags &= ~L.CONV_DX_ACCUMULATE
     dx = torch.empty((desc.N, desc.H, desc.W, desc.C), dtype=dy.dtype, device=dev)
     ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 1), dev)
     L.call("b2_pconv_dgrad", C.byref(desc), L.ptr(dy), L.ptr(ratio), L.ptr(wk), L.ptr(mask), L.ptr(dx),
            L.ptr(ws), wsn, L.stream())
-    return dx
+    return dx if addend is None else dx + addend
 
 
 def _conv_wgrad(desc, x, mask, dy, ratio, sink=None):
@@ -196,7 +212,12 @@ class ConvBNFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, mask, weight, shadow, gamma, beta, running_mean, running_var, residual, cfg, sinks=None):
+    def forward(ctx, x, mask, weight, shadow, gamma, beta, running_mean, running_var, residual, cfg, sinks=None,
+                dx_holder=None, res_holder=None):
+        # dx_holder / res_holder: a dict shared by the first and the last conv+BN node of a residual
+        # block with identity shortcut.  The last node parks the shortcut's gradient there instead of
+        # returning it; the first node (whose backward always runs later) folds it into its dx with a
+        # TMA reduce-add, so autograd never launches a separate add over the block input's gradient.
         stride, pad, dil, partial, premasked, relu, mask_output, training, momentum, eps, force_ffma = cfg
         L.require_cuda(x, mask, weight, gamma)
         x = x.contiguous()
@@ -222,6 +243,7 @@ class ConvBNFn(Function):
         ctx.desc, ctx.relu, ctx.training, ctx.wdtype = desc, relu, training, weight.dtype
         ctx.has_res = residual is not None
         ctx.sinks = sinks
+        ctx.dx_holder, ctx.res_holder = dx_holder, res_holder
         # z is only needed for the ReLU gate of residual layers; otherwise the gate is recomputed from y
         ctx.save_for_backward(x, mask if partial else None, wk, ratio, y, z if (relu and residual is not None) else None,
                               mean, invstd, gamma.detach(), beta.detach(), row_mask)
@@ -256,7 +278,8 @@ class ConvBNFn(Function):
         desc.flags |= L.CONV_DY_PRESCALED
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = _conv_dgrad(desc, dy, None, wk, mask)
+            addend = ctx.dx_holder.pop("dres", None) if ctx.dx_holder is not None else None
+            dx = _conv_dgrad(desc, dy, None, wk, mask, addend)
         if ctx.needs_input_grad[2]:
             dw = _conv_wgrad(desc, x, mask, dy, None, sinks[0] if sinks is not None else None)
             if dw is not None:
@@ -264,7 +287,10 @@ class ConvBNFn(Function):
         desc.flags &= ~L.CONV_DY_PRESCALED
         if sinks is not None:
             dgamma = dbeta = None
-        return dx, None, dw, None, dgamma, dbeta, None, None, dres, None, None
+        if dres is not None and ctx.res_holder is not None:
+            ctx.res_holder["dres"] = dres          # delivered through the block's first node
+            dres = None
+        return dx, None, dw, None, dgamma, dbeta, None, None, dres, None, None, None, None
 
 
 class MaxPoolFn(Function):

@@ -48,7 +48,9 @@ enum {
   B2_CONV_X_PREMASKED = 2,   /* caller guarantees x == x*mask_in (skip the multiply)           */
   B2_CONV_DY_PRESCALED = 4,  /* dgrad/wgrad: dy already multiplied by `ratio`                  */
   B2_CONV_FORCE_FFMA = 8,    /* debugging / fp32-accurate path even for bf16 tensors           */
-  B2_CONV_RELU_IN = 16       /* reserved                                                       */
+  B2_CONV_DX_ACCUMULATE = 16 /* dgrad: dx += result (bf16 TMA reduce-add) -- folds the gradient of */
+                             /* a residual branch into the block input's gradient; tensor-core     */
+                             /* path with stride 1 and C % 64 == 0 only, B2_E_UNSUPPORTED otherwise */
 };
 
 typedef struct B2ConvDesc {

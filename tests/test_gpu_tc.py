@@ -112,3 +112,30 @@ def test_tc_matches_ffma_bits_of_mask_and_ratio(b2pose, dev):
         outs.append((y, mo, ratio))
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
     assert rel_err(outs[0][0], outs[1][0]) < 1e-2
+
+
+def test_dgrad_reduce_add(b2pose, dev):
+    """B2_CONV_DX_ACCUMULATE: dx += dgrad(...) through the TMA reduce-add epilogue equals a separate
+    bf16 add (this folds the identity-shortcut gradient of a residual block into its first conv)."""
+    L = b2pose._lib
+    gen = torch.Generator().manual_seed(12)
+    for (N, H, W, Cin, K, k, p, d, partial) in [(2, 16, 16, 256, 64, 1, 0, 1, False), (2, 16, 16, 64, 64, 3, 1, 1, False),
+                                                (2, 12, 12, 128, 128, 3, 2, 2, False), (2, 16, 16, 256, 64, 1, 0, 1, True)]:
+        flags = L.CONV_PARTIAL if partial else 0
+        desc = b2pose.ops.make_desc((N, H, W, Cin), K, k, k, 1, p, d, L.BF16, flags)
+        dy = torch.randn(N, desc.Ho, desc.Wo, K, generator=gen).to(dev).bfloat16()
+        w = (torch.randn(K, k, k, Cin, generator=gen) * 0.05).to(dev).bfloat16()
+        mask = (torch.rand(N, H, W, generator=gen) > 0.3).float().to(dev) if partial else None
+        ratio = torch.rand(N, desc.Ho, desc.Wo, generator=gen).to(dev) if partial else None
+        addend = torch.randn(N, H, W, Cin, generator=gen).to(dev).bfloat16()
+        plain = b2pose.ops._conv_dgrad(desc, dy, ratio, w, mask)
+        fused = b2pose.ops._conv_dgrad(desc, dy, ratio, w, mask, addend.clone())
+        want = plain + addend
+        assert rel_err(fused, want) < 4e-3, (Cin, K, k)           # one bf16 rounding at most
+    # a shape the reduce-add epilogue does not take falls back to a separate add
+    desc = b2pose.ops.make_desc((2, 17, 17, 128), 128, 3, 3, 2, 1, 1, L.BF16, 0)
+    dy = torch.randn(2, desc.Ho, desc.Wo, 128, generator=gen).to(dev).bfloat16()
+    w = (torch.randn(128, 3, 3, 128, generator=gen) * 0.05).to(dev).bfloat16()
+    addend = torch.randn(2, 17, 17, 128, generator=gen).to(dev).bfloat16()
+    got = b2pose.ops._conv_dgrad(desc, dy, None, w, None, addend.clone())
+    assert rel_err(got, b2pose.ops._conv_dgrad(desc, dy, None, w, None) + addend) < 4e-3
