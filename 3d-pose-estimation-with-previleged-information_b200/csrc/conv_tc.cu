@@ -643,47 +643,60 @@ __global__ void tap_transpose_kernel(const bf16* __restrict__ w, bf16* __restric
 
 // ------------------------------------------------------------------ stem: im2col + padded filter
 // col[pix][(r*S+s)*C + c] = x[n, oh*st-p+r*dil, ow*st-p+s*dil, c] (* mask) ; columns >= R*S*C are zero.
-// One CTA per output row: the R input rows it needs are staged in shared memory (coalesced reads,
-// zero borders, mask applied), then every thread assembles 16-byte column chunks from shared memory
-// and writes them coalesced.
+// One CTA per output row: the R input rows it needs are staged in shared memory as bf16 (coalesced
+// reads, zero borders, mask applied) together with a column -> patch-offset table, then every thread
+// assembles 16-byte column chunks from shared memory (no divisions in the inner loop) and writes them
+// coalesced.  The kernel is bound by the write of the matrix.
+template <int C>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ col, int N, int H, int W,
-              int C, int R, int S, int stride, int pad, int dil, int Ho, int Wo, int Kpad) {
-  extern __shared__ float rows_sm[];            // [R][Wp*C], Wp = W + 2*pad
+              int R, int S, int stride, int pad, int dil, int Ho, int Wo, int Kpad) {
+  extern __shared__ __align__(16) uint8_t im_smem[];
   const int Wp = W + 2 * pad, rowlen = Wp * C;
+  bf16* rows_sm = reinterpret_cast<bf16*>(im_smem);                 // [R][rowlen]
+  int* off_sm = reinterpret_cast<int*>(im_smem + (((size_t)R * rowlen * 2 + 15) & ~(size_t)15));   // [Kpad]
   const int oh = blockIdx.x % Ho, n = blockIdx.x / Ho;
-  for (int i = threadIdx.x; i < R * rowlen; i += blockDim.x) {
-    const int r = i / rowlen, j = i - r * rowlen;
-    const int iw = j / C - pad, c = j - (j / C) * C;
-    const int ih = oh * stride - pad + r * dil;
-    float v = 0.f;
-    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-      const long long ip = ((long long)n * H + ih) * W + iw;
-      v = __bfloat162float(x[ip * C + c]);
-      if (mask) v *= mask[ip];
+  const int RSC = R * S * C, SC = S * C;
+  for (int cidx = threadIdx.x; cidx < Kpad; cidx += blockDim.x) {
+    int o = -1;                                                      // -1: zero column (padding of the matrix)
+    if (cidx < RSC) {
+      const int r = cidx / SC, rem = cidx - r * SC, s2 = rem / C, c = rem - s2 * C;
+      o = r * rowlen + s2 * dil * C + c;
     }
-    rows_sm[i] = v;
+    off_sm[cidx] = o;
+  }
+  for (int r = 0; r < R; ++r) {
+    const int ih = oh * stride - pad + r * dil;
+    const bool row_ok = ih >= 0 && ih < H;
+    const long long rowbase = ((long long)n * H + ih) * W;
+    for (int j = threadIdx.x; j < rowlen; j += blockDim.x) {
+      const int pw = j / C, c = j - pw * C, iw = pw - pad;           // C is a compile-time constant
+      float v = 0.f;
+      if (row_ok && iw >= 0 && iw < W) {
+        v = __bfloat162float(x[(rowbase + iw) * C + c]);
+        if (mask) v *= mask[rowbase + iw];
+      }
+      rows_sm[r * rowlen + j] = __float2bfloat16_rn(v);
+    }
   }
   __syncthreads();
-  const int chunks = Kpad >> 3, RSC = R * S * C, SC = S * C;
+  const int chunks = Kpad >> 3;
   const long long pix0 = ((long long)n * Ho + oh) * Wo;
+  const unsigned short* rs16 = reinterpret_cast<const unsigned short*>(rows_sm);
   for (int i = threadIdx.x; i < Wo * chunks; i += blockDim.x) {
     const int ow = i / chunks, ch = i - ow * chunks;
-    float f[8];
+    const int base = ow * stride * C;
+    uint32_t w4[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int cidx = ch * 8 + j;
-      float v = 0.f;
-      if (cidx < RSC) {
-        const int r = cidx / SC, rem = cidx - r * SC;       // rem = s*C + c
-        const int s2 = rem / C, c = rem - s2 * C;
-        v = rows_sm[r * rowlen + (ow * stride + s2 * dil) * C + c];
-      }
-      f[j] = v;
+    for (int j = 0; j < 4; ++j) {
+      const int o0 = off_sm[ch * 8 + 2 * j], o1 = off_sm[ch * 8 + 2 * j + 1];
+      const uint32_t lo = o0 >= 0 ? rs16[o0 + base] : 0u, hi = o1 >= 0 ? rs16[o1 + base] : 0u;
+      w4[j] = lo | (hi << 16);
     }
-    store8(col + (pix0 + ow) * Kpad + ch * 8, f);
+    *reinterpret_cast<uint4*>(col + (pix0 + ow) * Kpad + ch * 8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
   }
 }
+
 // ---- 7x7 stride-2 stem as a 4x4 stride-1 convolution over a space-to-depth view ------------------
 // xs[n, h', w', (a*2+b)*C + c] = x[n, 2h'+a-1, 2w'+b-1, c] (* mask), channels >= 4C are zero.  With
 // pad' = 1 the tap (t, a) of the 4x4 view is the original tap r = 2t + a (r = 7 does not exist: zero
@@ -950,7 +963,12 @@ inline bool is_stem(const B2ConvDesc* d) { return d->C <= 4 && d->R * d->S * d->
 // the networks' stems: 7x7, stride 2, pad 3 -> 4x4 stride-1 convolution over the space-to-depth view
 inline bool is_s2d_stem(const B2ConvDesc* d) {
   // (C >= 3: for one input channel the im2col matrix is only 56 columns wide and measures faster)
-  return is_stem(d) && d->C >= 3 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->dil == 1;
+  // Measured (N64, 256x256x3 -> 64): space-to-depth 0.40 ms fprop / 0.57 ms wgrad, im2col + GEMM 0.29 / 0.39 ms
+  // (16 thin k-steps per tile versus 3 dense ones), so the im2col route is the default; B2POSE_STEM_S2D=1
+  // selects the space-to-depth route.
+  static const int mode = getenv("B2POSE_STEM_S2D") ? atoi(getenv("B2POSE_STEM_S2D")) : 0;
+  return mode != 0 && is_stem(d) && d->C >= 3 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 &&
+         d->dil == 1;
 }
 inline int s2d_cp(const B2ConvDesc* d) { return (4 * d->C + 7) / 8 * 8; }
 inline int s2d_h2(const B2ConvDesc* d) { return (d->H + 2) / 2; }
@@ -971,11 +989,16 @@ int launch_s2d(const B2ConvDesc* d, const void* x, const float* mask, bf16* xs, 
 
 int launch_im2col(const B2ConvDesc* d, const void* x, const float* mask, bf16* col, cudaStream_t st) {
   const int kpad = stem_kpad(d);
-  const size_t sh = (size_t)d->R * (d->W + 2 * d->pad) * d->C * sizeof(float);
+  const size_t sh = (((size_t)d->R * (d->W + 2 * d->pad) * d->C * 2 + 15) & ~(size_t)15) + (size_t)kpad * sizeof(int);
   B2_REQUIRE(sh <= 200 * 1024, B2_E_UNSUPPORTED, "im2col: input row too wide for shared memory");
-  if (sh > 48 * 1024) cudaFuncSetAttribute(im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-  im2col_kernel<<<d->N * d->Ho, 256, sh, st>>>((const bf16*)x, mask, col, d->N, d->H, d->W, d->C, d->R, d->S, d->stride,
-                                             d->pad, d->dil, d->Ho, d->Wo, kpad);
+#define IM2COL(CC)                                                                                              \
+  do {                                                                                                          \
+    if (sh > 48 * 1024) cudaFuncSetAttribute(im2col_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
+    im2col_kernel<CC><<<d->N * d->Ho, 256, sh, st>>>((const bf16*)x, mask, col, d->N, d->H, d->W, d->R, d->S,    \
+                                                    d->stride, d->pad, d->dil, d->Ho, d->Wo, kpad);            \
+  } while (0)
+  if (d->C == 1) IM2COL(1); else if (d->C == 2) IM2COL(2); else if (d->C == 3) IM2COL(3); else IM2COL(4);
+#undef IM2COL
   B2_LAUNCH_CHECK("im2col");
   return B2_OK;
 }
@@ -1011,6 +1034,7 @@ size_t conv_tc_workspace_bytes(const B2ConvDesc* d, int op) {
     const size_t kpad = stem_kpad(d);
     ws += align256((size_t)d->N * d->Ho * d->Wo * kpad * 2);            // im2col matrix
     ws += align256((size_t)d->K * kpad * (op == 2 ? 4 : 2));            // padded filter / padded dw
+    if (op == 0 && partial) ws += align256((size_t)d->N * d->Ho * d->Wo * 4);   // renormalisation ratio
     if (op == 2 && partial && !(d->flags & B2_CONV_DY_PRESCALED)) ws += dy_bytes;
     return ws;
   }
@@ -1026,6 +1050,7 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
                   void* y, float* mask_out, float* ratio_out, float* bn_sums, void* workspace, cudaStream_t st) {
   RunArgs a{};
   const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
+  const float* stem_ratio = nullptr;
   a.act = x; a.N = d->N; a.H = d->H; a.W = d->W; a.C = d->C;
   a.filt = w; a.K = d->K; a.R = d->R; a.S = d->S; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
   if (is_s2d_stem(d)) {
@@ -1047,10 +1072,22 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
     pad_filter_kernel<<<(d->K * kpad + 255) / 256, 256, 0, st>>>((const bf16*)w, wp, d->K, d->R * d->S * d->C, kpad);
     B2_LAUNCH_CHECK("pad_filter");
     a.act = col; a.H = d->Ho; a.W = d->Wo; a.C = kpad; a.filt = wp; a.R = 1; a.S = 1; a.stride = 1; a.pad = 0; a.dil = 1;
+    if (partial) {
+      // a 7x7 window is 49 mask loads per output pixel: do the mask algebra once in its own small
+      // kernel and let the GEMM epilogue read the ratio as a per-row scale
+      float* rbuf = ratio_out ? ratio_out
+                              : (float*)((uint8_t*)wp + align256((size_t)d->K * kpad * 2));
+      rc = b2_pconv_mask_update(d, mask_in, mask_out, rbuf, (void*)st);
+      if (rc) return rc;
+      stem_ratio = rbuf;
+    }
   }
   a.Ho = d->Ho; a.Wo = d->Wo; a.out = y; a.out_H = d->Ho; a.out_W = d->Wo; a.out_stride_sp = 1;
   a.scale_mode = partial ? 1 : 0;
   a.mask_in = mask_in; a.bias = bias; a.mask_out = mask_out; a.ratio_out = ratio_out;
+  if (stem_ratio) {
+    a.scale_mode = 2; a.row_scale = stem_ratio; a.mask_out = nullptr; a.ratio_out = nullptr;
+  }
   a.mask_R = d->R; a.mask_S = d->S; a.mask_stride = d->stride; a.mask_pad = d->pad; a.mask_dil = d->dil;
   a.mask_H = d->H; a.mask_W = d->W;
   bool fused = false;
