@@ -73,6 +73,42 @@ __device__ __forceinline__ void store8(bf16* p, const float* f) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 issue two fp32 operations per lane and
+// instruction, which matters in the issue-bound convolution epilogue)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// two bf16 in one 32-bit word -> packed fp32x2 (exact)
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t w) {
+  return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+// two fp32 -> two bf16 (round to nearest even) in one 32-bit word, `lo` in the low half
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

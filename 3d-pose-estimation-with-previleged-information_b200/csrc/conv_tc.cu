@@ -266,6 +266,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int brick = p.BW * p.BH;
     const int groups = p.BN >> 6;
     const int nsets = p.tma_store ? kStaging / groups : 1;      // staging sets of `groups` 16 KB buffers
+    uint64_t st_sum[2][4], st_sq[2][4];           // fused BatchNorm statistics (packed fp32x2), see below
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) st_sum[k][e] = st_sq[k][e] = 0ull;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
@@ -324,7 +329,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           else bulk_wait_read<0>();
         }
         epi_barrier();
-        // software-pipelined TMEM reads: the loads of group g+1 are in flight while group g is converted
+        // software-pipelined TMEM reads: the loads of group g+1 are in flight while group g is converted.
+        // The epilogue is instruction-issue bound on the shallow layers (8 warps on 4 schedulers), so the
+        // conversion uses packed fp32x2 multiplies and skips the multiply when there is no row scale:
+        // out-of-range rows of a ragged tile are zero in TMEM already (TMA zero-fills the A operand) and
+        // clipped by the TMA store.
+        const float sc = valid ? scale : 0.f;
+        const uint64_t sc2 = pack2(sc, sc);
+        const bool unit = p.scale_mode == 0;
         uint32_t va[32], vb[32];
         tmem_ld16(taddr + half * 32, va);
         tmem_ld16(taddr + half * 32 + 16, va + 16);
@@ -339,12 +351,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sbuf = sset + (size_t)g * kABytes;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float f[8];
+            uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = valid ? __uint_as_float(v[j * 8 + e]) * scale : 0.f;
+            for (int e = 0; e < 4; ++e) {
+              float a = __uint_as_float(v[j * 8 + 2 * e]), b = __uint_as_float(v[j * 8 + 2 * e + 1]);
+              if (!unit) unpack2(mul2(pack2(a, b), sc2), a, b);
+              w[e] = f32x2_to_bf16x2(a, b);
+            }
             const int chunk = half * 4 + j;
-            if (!(p.debug & 8)) store8(reinterpret_cast<bf16*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)), f);
-            else if (f[0] == 12345.678f) p.out[0] = __float2bfloat16(f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7]);
+            *reinterpret_cast<uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
         tc_fence_before();                        // accumulator fully read: hand TMEM back to the MMA warp
@@ -364,43 +379,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           bulk_commit();
         }
         if (p.bn_sums && !(p.debug & 4)) {
-          // per-channel sum / sum of squares of the staged tile: 16-byte shared loads (a quarter-warp
-          // reads one whole 128-byte row), two shuffle steps, warp-private fp32 accumulators
-          const int chunk = ep_tid & 7, rsub = ep_tid >> 3;        // rsub 0..31
+          // per-channel sum / sum of squares of the staged (rounded) tile.  Thread (chunk, ghalf, rsub)
+          // owns 8 channels of the 64-channel groups ghalf and ghalf + 2 and rows rsub, rsub + 16, ...:
+          // 16-byte shared loads (a quarter-warp reads one whole 128-byte row), packed fp32x2 adds / fmas
+          // into registers that live across ALL tiles of this CTA (tiles_k == 1) -- no shuffles, no
+          // shared-memory read-modify-writes per tile.
+          const int chunk = ep_tid & 7, ghalf = (ep_tid >> 3) & 1, rsub = ep_tid >> 4;        // rsub 0..15
           const int nrows = min(brick * p.BNI, kTileM);
-          float* mine = s_stats + (size_t)ew * 2 * p.K;
-          for (int g = 0; g < groups; ++g) {
-            const uint8_t* sbuf = sset + (size_t)g * kABytes;
-            float su[8], sq[8];
+          const uint32_t off = (uint32_t)rsub * 128u + (uint32_t)((chunk ^ (rsub & 7)) << 4);   // (rsub + 16 i) & 7 == rsub & 7
 #pragma unroll
-            for (int e = 0; e < 8; ++e) su[e] = sq[e] = 0.f;
+          for (int k = 0; k < 2; ++k) {
+            const int g = ghalf + 2 * k;
+            if (g < groups) {
+              const uint8_t* sbuf = sset + (size_t)g * kABytes + off;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = rsub + 32 * i;
-              if (r < nrows) {
-                float t[8];
-                load8(reinterpret_cast<const bf16*>(sbuf + r * 128 + ((chunk ^ (r & 7)) << 4)), t);
+              for (int i = 0; i < 8; ++i) {
+                if (rsub + 16 * i < nrows) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(sbuf + i * 2048);
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { su[e] += t[e]; sq[e] = fmaf(t[e], t[e], sq[e]); }
+                  for (int e = 0; e < 4; ++e) {
+                    const uint64_t t = bf16x2_to_f32x2(w[e]);
+                    st_sum[k][e] = add2(st_sum[k][e], t);
+                    st_sq[k][e] = fma2(t, t, st_sq[k][e]);
+                  }
+                }
               }
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              su[e] += __shfl_xor_sync(0xffffffffu, su[e], 8);
-              sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 8);
-              su[e] += __shfl_xor_sync(0xffffffffu, su[e], 16);
-              sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
-            }
-            const int ch0 = kbase + g * 64 + chunk * 8;
-            if (lane < 8 && ch0 < p.K) {           // 16-byte read-modify-writes of the warp-private partials
-              float4* ps = reinterpret_cast<float4*>(mine + ch0);
-              float4* pq = reinterpret_cast<float4*>(mine + p.K + ch0);
-              float4 s0 = ps[0], s1 = ps[1], q0 = pq[0], q1 = pq[1];
-              s0.x += su[0]; s0.y += su[1]; s0.z += su[2]; s0.w += su[3];
-              s1.x += su[4]; s1.y += su[5]; s1.z += su[6]; s1.w += su[7];
-              q0.x += sq[0]; q0.y += sq[1]; q0.z += sq[2]; q0.w += sq[3];
-              q1.x += sq[4]; q1.y += sq[5]; q1.z += sq[6]; q1.w += sq[7];
-              ps[0] = s0; ps[1] = s1; pq[0] = q0; pq[1] = q1;
             }
           }
         }
@@ -437,6 +441,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (lane == 0) mbar_arrive(&bars->tempty[acc]);
     }
     if (p.tma_store && threadIdx.x == 64) bulk_wait_read<0>();     // staging must outlive the last store
+    if (p.bn_sums) {
+      // lanes l and l ^ 16 hold the same channels (rows rsub and rsub ^ 1): combine, then the low half-warp
+      // writes this warp's partial; the 8 warp partials are summed in a fixed order below (deterministic)
+      const int chunk = ep_tid & 7, ghalf = (ep_tid >> 3) & 1;
+      float* mine = s_stats + (size_t)ew * 2 * p.K;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float su[8], sq[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          unpack2(st_sum[k][e], su[2 * e], su[2 * e + 1]);
+          unpack2(st_sq[k][e], sq[2 * e], sq[2 * e + 1]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          su[e] += __shfl_xor_sync(0xffffffffu, su[e], 16);
+          sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
+        }
+        const int g = ghalf + 2 * k;
+        if (lane < 16 && g < groups) {
+          const int ch0 = g * 64 + chunk * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { mine[ch0 + e] = su[e]; mine[p.K + ch0 + e] = sq[e]; }
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -896,14 +926,14 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   const int stage_bytes = (int)kABytes + p.BN * kBlockK * 2;
   static const bool no_tma_store = getenv("B2POSE_TC_NO_TMA_STORE") != nullptr;      // tuning switches
   static const bool no_fused_stats = getenv("B2POSE_TC_NO_FUSED_STATS") != nullptr;
-  p.tma_store = (p.BN % 64 == 0 && a.out_stride_sp == 1 && !no_tma_store) ? 1 : 0;
+  p.tma_store = (p.BN % 64 == 0 && a.out_stride_sp == 1 && !a.bias && !no_tma_store) ? 1 : 0;   // bias: direct-store path
   static const int env_debug = getenv("B2POSE_TC_DEBUG") ? atoi(getenv("B2POSE_TC_DEBUG")) : 0;
   p.debug = env_debug;
   p.accumulate = a.accumulate;
   B2_REQUIRE(!a.accumulate || p.tma_store, B2_E_UNSUPPORTED,
              "conv_tc: accumulate needs the TMA-store epilogue (output channels %% 64 == 0, stride 1)");
   // fused statistics for the wide-spatial layers (K <= 256); deeper layers are small and keep the separate pass
-  p.bn_sums = (p.tma_store && a.bn_sums && a.K <= 256 && !no_fused_stats) ? a.bn_sums : nullptr;
+  p.bn_sums = (p.tma_store && a.bn_sums && a.K <= 256 && p.tiles_k == 1 && !no_fused_stats) ? a.bn_sums : nullptr;
   if (a.stats_fused) *a.stats_fused = p.bn_sums != nullptr;
   const int extra = (p.tma_store ? kStaging * (int)kABytes : 0) + (p.bn_sums ? 64 * a.K : 0);
   int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars) - extra) / stage_bytes;
