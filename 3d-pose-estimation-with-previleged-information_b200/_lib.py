@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2pose.so")
 
 F32, BF16 = 0, 1
-CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA, CONV_DX_ACCUMULATE = 1, 2, 4, 8, 16
-ABI_VERSION = 2
+CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA, CONV_DX_ACCUMULATE, CONV_BN_TOTALS = 1, 2, 4, 8, 16, 32
+ABI_VERSION = 3
 BN_PARTS = 320
 
 
@@ -47,6 +47,11 @@ SIGNATURES = {
     "b2_bn_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _l, _i, _i, _p],
     "b2_bn_bwd_finalize": [_p, _i, _p, _p, _p, _p],
     "b2_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _l, _i, _i, _p],
+    "b2_bn_totals_supported": [_i, _i],
+    "b2_bn_stats_totals": [_p, _l, _i, _i, _p, _p],
+    "b2_bn_apply_totals": [_p, _p, _l, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _p],
+    "b2_bn_bwd_reduce_totals": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _l, _i, _i, _p],
+    "b2_bn_bwd_apply_totals": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p],
     "b2_maxpool3x3s2_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2_maxpool3x3s2_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2_head_fwd": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],

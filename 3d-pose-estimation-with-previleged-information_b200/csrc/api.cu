@@ -63,6 +63,8 @@ extern "C" int b2_pconv_fprop(const B2ConvDesc* d, const void* x, const float* m
   }
   rc = conv_ffma_fprop(d, x, mask_in, w, bias, y, mask_out, ratio_out, st);
   if (rc) return rc;
+  if (bn_sums && (d->flags & B2_CONV_BN_TOTALS))
+    return b2_bn_stats_totals(y, (int64_t)d->N * d->Ho * d->Wo, d->K, d->dtype, bn_sums, stream);
   if (bn_sums) return b2_bn_stats(y, (int64_t)d->N * d->Ho * d->Wo, d->K, d->dtype, bn_sums, stream);
   return B2_OK;
 }

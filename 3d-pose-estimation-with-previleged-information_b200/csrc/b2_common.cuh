@@ -192,14 +192,18 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
 
 // bulk-async (TMA 1-D) staged BatchNorm stream kernels for bf16, C a power of two in [64, 2048] (bn_stream.cu)
 bool bn_stream_eligible(int C, int dtype);
-int bn_stream_stats(const void* y, int64_t rows, int C, float* partials, cudaStream_t st);
+int bn_stream_stats(const void* y, int64_t rows, int C, float* partials, int totals, cudaStream_t st);
+int bn_stream_apply_fin(const void* y, const void* residual, void* z, const float* mean, const float* invstd,
+                        const float* gamma, const float* beta, const float* row_mask, int relu, int64_t rows, int C,
+                        int mode, const float* totals, float* running_mean, float* running_var, float momentum,
+                        float eps, float* mean_out, float* invstd_out, cudaStream_t st);
 int bn_stream_apply(const void* y, const void* residual, void* z, const float* mean, const float* invstd,
                     const float* gamma, const float* beta, const float* row_mask, int relu, int64_t rows, int C,
                     cudaStream_t st);
 int bn_stream_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const float* row_mask, int relu, float* partials,
-                         int64_t rows, int C, cudaStream_t st);
+                         int totals, int64_t rows, int C, cudaStream_t st);
 int bn_stream_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, const float* gsum, const float* row_mask,
-                        const float* row_scale, int relu, int training, void* dy, void* d_residual, int64_t rows,
-                        int C, cudaStream_t st);
+                        const float* row_scale, int relu, int training, void* dy, void* d_residual, float* dgamma,
+                        float* dbeta, int64_t rows, int C, cudaStream_t st);

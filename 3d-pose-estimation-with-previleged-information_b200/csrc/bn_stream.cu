@@ -86,8 +86,12 @@ __device__ __forceinline__ void ring_setup(Ring<NIN>& r, uint8_t* smem, long lon
 
 // block-level reduction of per-thread partials (8 channels x 2 quantities) that share a channel
 // vector across the thread groups of the block; writes this block's slot (see bn.cu)
+//
+// totals != 0: `partials` is ONE pre-zeroed float[2C] vector and every block adds its sums with
+// red.global.add.f32 (2C reductions per block); the consumers derive mean / invstd (or use the gradient
+// sums) in their prologue, so no finalize kernel sits between producer and consumer.
 __device__ __forceinline__ void slot_reduce(const float* s, const float* q, float* __restrict__ partials, int C,
-                                            int cv, int CV, float* red) {
+                                            int cv, int CV, float* red, int totals) {
   // red: [2][kThreadsS][8]
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -95,22 +99,25 @@ __device__ __forceinline__ void slot_reduce(const float* s, const float* q, floa
     red[(kThreadsS + threadIdx.x) * 8 + j] = q[j];
   }
   __syncthreads();
-  float* slot = partials + (size_t)blockIdx.x * 2 * C;
+  float* slot = partials + (totals ? (size_t)0 : (size_t)blockIdx.x * 2 * C);
   // thread t < 2*C handles one output value: quantity = t / C, channel = t % C
   for (int o = threadIdx.x; o < 2 * C; o += kThreadsS) {
     const int qn = o / C, c = o - qn * C, v = c >> 3, j = c & 7;
     float acc = 0.f;
     for (int t = v; t < kThreadsS; t += CV) acc += red[(qn * kThreadsS + t) * 8 + j];
-    slot[o] = acc;
+    if (totals) atomicAdd(slot + o, acc);
+    else slot[o] = acc;
   }
-  for (int sl = gridDim.x + blockIdx.x; sl < B2_BN_PARTS; sl += gridDim.x)
-    for (int o = threadIdx.x; o < 2 * C; o += kThreadsS) partials[(size_t)sl * 2 * C + o] = 0.f;
+  if (!totals)
+    for (int sl = gridDim.x + blockIdx.x; sl < B2_BN_PARTS; sl += gridDim.x)
+      for (int o = threadIdx.x; o < 2 * C; o += kThreadsS) partials[(size_t)sl * 2 * C + o] = 0.f;
   (void)cv;
 }
 
 // ---------------------------------------------------------------- stats
 __global__ void __launch_bounds__(kThreadsS, 3)
-stats_stream_kernel(const bf16* __restrict__ y, long long total_elems, int C, float* __restrict__ partials) {
+stats_stream_kernel(const bf16* __restrict__ y, long long total_elems, int C, float* __restrict__ partials,
+                    int totals) {
   pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   Ring<1> ring;
@@ -147,15 +154,28 @@ stats_stream_kernel(const bf16* __restrict__ y, long long total_elems, int C, fl
     if (threadIdx.x == 0 && nxt < chunks) ring.issue(stage, nxt);
     if (++stage == kStagesS) { stage = 0; phase ^= 1; }
   }
-  slot_reduce(s, q, partials, C, cv, CV, red);
+  slot_reduce(s, q, partials, C, cv, CV, red, totals);
 }
 
 // ---------------------------------------------------------------- apply
+// mode 0: mean / invstd given; 1: derive them from totals[2C] (block 0 also writes mean_out / invstd_out and
+// updates the running statistics, BatchNorm2d training semantics); 2: frozen running statistics
+struct ApplyFin {
+  int mode;
+  const float* totals;
+  long long rows;
+  float* running_mean;
+  float* running_var;
+  float momentum, eps;
+  float* mean_out;
+  float* invstd_out;
+};
+
 __global__ void __launch_bounds__(kThreadsS, 3)
 apply_stream_kernel(const bf16* __restrict__ y, const bf16* __restrict__ residual, bf16* __restrict__ z,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ row_mask, int relu,
-                    long long total_elems, int C) {
+                    long long total_elems, int C, const ApplyFin fin) {
   pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   const int CV = C >> 3, cv = threadIdx.x % CV, logC = 31 - __clz(C);
@@ -164,8 +184,29 @@ apply_stream_kernel(const bf16* __restrict__ y, const bf16* __restrict__ residua
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cv * 8 + j;
-    sc[j] = invstd[c] * gamma[c];
-    sh[j] = beta[c] - mean[c] * sc[j];
+    float mu, is;
+    if (fin.mode == 0) {                       // finalized by a separate kernel
+      mu = mean[c]; is = invstd[c];
+    } else {
+      if (fin.mode == 1) {                     // batch statistics from the producers' totals
+        const double n = (double)fin.rows, m = (double)fin.totals[c] / n;
+        double var = (double)fin.totals[C + c] / n - m * m;
+        if (var < 0) var = 0;
+        mu = (float)m;
+        is = (float)(1.0 / sqrt(var + (double)fin.eps));
+        if (blockIdx.x == 0 && threadIdx.x < CV && fin.running_mean) {
+          const double unbiased = n > 1 ? var * n / (n - 1) : var;
+          fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * mu;
+          fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unbiased;
+        }
+      } else {                                 // frozen statistics (eval)
+        mu = fin.running_mean[c];
+        is = 1.f / sqrtf(fin.running_var[c] + fin.eps);
+      }
+      if (blockIdx.x == 0 && threadIdx.x < CV) { fin.mean_out[c] = mu; fin.invstd_out[c] = is; }
+    }
+    sc[j] = is * gamma[c];
+    sh[j] = beta[c] - mu * sc[j];
   }
   const long long chunks = (total_elems * 2 + kChunkBytes - 1) / kChunkBytes;
   auto body = [&](auto& ring, bool has_res) {
@@ -223,6 +264,8 @@ struct BwdArgs {
   int relu, training;
   bf16 *dy, *d_residual;
   float* partials;
+  int totals;                  // reduce: partials is a pre-zeroed float[2C] (atomic adds)
+  float *dgamma, *dbeta;       // apply: block 0 accumulates the affine gradients from gsum
   long long total_elems, rows;
   int C;
 };
@@ -257,6 +300,10 @@ __global__ void __launch_bounds__(kThreadsS, 3) bwd_stream_kernel(const BwdArgs 
       k0[j] = ga;                       // A
       k1[j] = -ga * is * mgx;           // B
       k2[j] = -ga * mg - mu * k1[j];    // D
+      if (blockIdx.x == 0 && threadIdx.x < CV) {
+        if (a.dgamma) a.dgamma[c] += a.gsum[C + c];
+        if (a.dbeta) a.dbeta[c] += a.gsum[c];
+      }
     }
   }
   float s[8], q[8];
@@ -316,7 +363,7 @@ __global__ void __launch_bounds__(kThreadsS, 3) bwd_stream_kernel(const BwdArgs 
   if (MODE == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) q[j] *= k1[j];
-    slot_reduce(s, q, a.partials, C, cv, CV, red);
+    slot_reduce(s, q, a.partials, C, cv, CV, red, a.totals);
   }
 }
 
@@ -356,12 +403,12 @@ bool bn_stream_eligible(int C, int dtype) {
   return enabled() && dtype == B2_BF16 && C >= 64 && C <= 2048 && (C & (C - 1)) == 0;
 }
 
-int bn_stream_stats(const void* y, int64_t rows, int C, float* partials, cudaStream_t st) {
+int bn_stream_stats(const void* y, int64_t rows, int C, float* partials, int totals, cudaStream_t st) {
   const size_t sh = smem_bytes(1, true);
   int rc = opt_in(stats_stream_kernel, sh);
   if (rc) return rc;
   launch_pdl(stats_stream_kernel, dim3(stream_grid(rows * C, 2, true)), dim3(kThreadsS), sh, st, (const bf16*)y,
-             (long long)(rows * C), C, partials);
+             (long long)(rows * C), C, partials, totals);
   B2_LAUNCH_CHECK("bn_stats(stream)");
   return B2_OK;
 }
@@ -369,11 +416,23 @@ int bn_stream_stats(const void* y, int64_t rows, int C, float* partials, cudaStr
 int bn_stream_apply(const void* y, const void* residual, void* z, const float* mean, const float* invstd,
                     const float* gamma, const float* beta, const float* row_mask, int relu, int64_t rows, int C,
                     cudaStream_t st) {
+  return bn_stream_apply_fin(y, residual, z, mean, invstd, gamma, beta, row_mask, relu, rows, C, 0, nullptr, nullptr,
+                             nullptr, 0.f, 0.f, nullptr, nullptr, st);
+}
+
+int bn_stream_apply_fin(const void* y, const void* residual, void* z, const float* mean, const float* invstd,
+                        const float* gamma, const float* beta, const float* row_mask, int relu, int64_t rows, int C,
+                        int mode, const float* totals, float* running_mean, float* running_var, float momentum,
+                        float eps, float* mean_out, float* invstd_out, cudaStream_t st) {
+  ApplyFin fin{};
+  fin.mode = mode; fin.totals = totals; fin.rows = rows; fin.running_mean = running_mean;
+  fin.running_var = running_var; fin.momentum = momentum; fin.eps = eps; fin.mean_out = mean_out;
+  fin.invstd_out = invstd_out;
   const size_t sh = smem_bytes(residual ? 2 : 1, false);
   int rc = opt_in(apply_stream_kernel, sh);
   if (rc) return rc;
   launch_pdl(apply_stream_kernel, dim3(stream_grid(rows * C, 3, false)), dim3(kThreadsS), sh, st, (const bf16*)y,
-             (const bf16*)residual, (bf16*)z, mean, invstd, gamma, beta, row_mask, relu, (long long)(rows * C), C);
+             (const bf16*)residual, (bf16*)z, mean, invstd, gamma, beta, row_mask, relu, (long long)(rows * C), C, fin);
   B2_LAUNCH_CHECK("bn_apply(stream)");
   return B2_OK;
 }
@@ -389,9 +448,9 @@ static BwdArgs make_bwd(const void* dz, const void* z, const void* y, const floa
 
 int bn_stream_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const float* row_mask, int relu, float* partials,
-                         int64_t rows, int C, cudaStream_t st) {
+                         int totals, int64_t rows, int C, cudaStream_t st) {
   BwdArgs a = make_bwd(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, rows, C);
-  a.partials = partials;
+  a.partials = partials; a.totals = totals;
   const bool hasz = relu && z != nullptr;
   const size_t sh = smem_bytes(hasz ? 3 : 2, true);
   const int grid = stream_grid(rows * C, 2, true);
@@ -409,9 +468,10 @@ int bn_stream_bwd_reduce(const void* dz, const void* z, const void* y, const flo
 
 int bn_stream_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, const float* gsum, const float* row_mask,
-                        const float* row_scale, int relu, int training, void* dy, void* d_residual, int64_t rows,
-                        int C, cudaStream_t st) {
+                        const float* row_scale, int relu, int training, void* dy, void* d_residual, float* dgamma,
+                        float* dbeta, int64_t rows, int C, cudaStream_t st) {
   BwdArgs a = make_bwd(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, rows, C);
+  a.dgamma = dgamma; a.dbeta = dbeta;
   a.gsum = gsum; a.row_scale = row_scale; a.training = training; a.dy = (bf16*)dy; a.d_residual = (bf16*)d_residual;
   const bool hasz = relu && z != nullptr;
   const size_t sh = smem_bytes(hasz ? 3 : 2, false);

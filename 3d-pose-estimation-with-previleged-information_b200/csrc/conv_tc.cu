@@ -162,6 +162,7 @@ struct FpropParams {
   int accumulate;                                      // TMA reduce-add into the output instead of a plain store
   int debug;                                           // tuning experiments (B2POSE_TC_DEBUG): 1 skip epilogue, 2 skip store, 4 skip B reload
   float* bn_sums;                                      // partials[B2_BN_PARTS][2*K]: sum / sum of squares of the stored output
+  int bn_totals;                                       // bn_sums is one pre-zeroed float[2*K]: add with fp32 reductions
 };
 
 struct __align__(8) PipeBars {
@@ -472,15 +473,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   if (p.bn_sums) {      // this CTA's slot of partials[B2_BN_PARTS][2K]; the unused slots are zero-filled
-    float* slot = p.bn_sums + (size_t)blockIdx.x * 2 * p.K;
+    float* slot = p.bn_sums + (p.bn_totals ? (size_t)0 : (size_t)blockIdx.x * 2 * p.K);
     for (int i = threadIdx.x; i < 2 * p.K; i += kConvThreads) {
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += s_stats[(size_t)w * 2 * p.K + i];
-      slot[i] = t;
+      if (p.bn_totals) atomicAdd(slot + i, t);
+      else slot[i] = t;
     }
-    for (int sl = gridDim.x + blockIdx.x; sl < B2_BN_PARTS; sl += gridDim.x)
-      for (int i = threadIdx.x; i < 2 * p.K; i += kConvThreads) p.bn_sums[(size_t)sl * 2 * p.K + i] = 0.f;
+    if (!p.bn_totals)
+      for (int sl = gridDim.x + blockIdx.x; sl < B2_BN_PARTS; sl += gridDim.x)
+        for (int i = threadIdx.x; i < 2 * p.K; i += kConvThreads) p.bn_sums[(size_t)sl * 2 * p.K + i] = 0.f;
   }
 }
 
@@ -900,7 +903,7 @@ struct RunArgs {
   void* out; int out_H, out_W, out_stride_sp, out_off_h, out_off_w;
   int pad_w, use_pad_w;                                        // pad_w is read only when use_pad_w != 0
   int accumulate;                                              // dgrad: reduce-add into `out`
-  float* bn_sums; bool* stats_fused;                          // optional fused BatchNorm statistics
+  float* bn_sums; bool* stats_fused; int bn_totals;           // optional fused BatchNorm statistics
   int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
   float* mask_out; float* ratio_out;
   int mask_R, mask_S, mask_stride, mask_pad, mask_dil, mask_H, mask_W;
@@ -934,6 +937,7 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
              "conv_tc: accumulate needs the TMA-store epilogue (output channels %% 64 == 0, stride 1)");
   // fused statistics for the wide-spatial layers (K <= 256); deeper layers are small and keep the separate pass
   p.bn_sums = (p.tma_store && a.bn_sums && a.K <= 256 && p.tiles_k == 1 && !no_fused_stats) ? a.bn_sums : nullptr;
+  p.bn_totals = a.bn_totals;
   if (a.stats_fused) *a.stats_fused = p.bn_sums != nullptr;
   const int extra = (p.tma_store ? kStaging * (int)kABytes : 0) + (p.bn_sums ? 64 * a.K : 0);
   int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars) - extra) / stage_bytes;
@@ -1121,10 +1125,14 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   a.mask_R = d->R; a.mask_S = d->S; a.mask_stride = d->stride; a.mask_pad = d->pad; a.mask_dil = d->dil;
   a.mask_H = d->H; a.mask_W = d->W;
   bool fused = false;
-  a.bn_sums = bn_sums; a.stats_fused = &fused;
+  a.bn_sums = bn_sums; a.stats_fused = &fused; a.bn_totals = (d->flags & B2_CONV_BN_TOTALS) ? 1 : 0;
   int rc = run_conv_tc(a, st);
   if (rc) return rc;
-  if (bn_sums && !fused) return b2_bn_stats(y, (int64_t)d->N * d->Ho * d->Wo, d->K, d->dtype, bn_sums, (void*)st);
+  if (bn_sums && !fused) {
+    if (d->flags & B2_CONV_BN_TOTALS)
+      return b2_bn_stats_totals(y, (int64_t)d->N * d->Ho * d->Wo, d->K, d->dtype, bn_sums, (void*)st);
+    return b2_bn_stats(y, (int64_t)d->N * d->Ho * d->Wo, d->K, d->dtype, bn_sums, (void*)st);
+  }
   return B2_OK;
 }
 

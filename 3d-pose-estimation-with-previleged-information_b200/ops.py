@@ -35,6 +35,64 @@ def bn_partials(C, device):
     return torch.empty(L.BN_PARTS * 2 * C, dtype=torch.float32, device=device)
 
 
+# ---- zeroed per-channel accumulators of the totals BatchNorm path --------------------------------
+# Producers ADD into float[2C] vectors; they are cut from one arena per device that the training step
+# zeroes once (`bn_arena_begin`), so a step costs one memset instead of two fills per layer.  Outside
+# a managed step (or when the arena is too small) a fresh zero tensor is returned instead.
+class _Arena:
+    __slots__ = ("buf", "off", "demand", "retired")
+
+    def __init__(self):
+        self.buf, self.off, self.demand, self.retired = None, 0, 0, []
+
+
+_arenas = {}
+_totals_ok = {}
+_BN_TOTALS = __import__("os").environ.get("B2POSE_BN_TOTALS", "1") != "0"
+
+
+def bn_totals_supported(C_, dtype):
+    key = (C_, dtype)
+    v = _totals_ok.get(key)
+    if v is None:
+        v = _BN_TOTALS and dtype == torch.bfloat16 and bool(L.lib().b2_bn_totals_supported(C_, L.BF16))
+        _totals_ok[key] = v
+    return v
+
+
+def bn_arena_begin(device):
+    """Start a training step: zero the arena (growing it to last step's demand first; never while a
+    CUDA graph is being captured, and retired buffers stay alive because captured graphs point at them)."""
+    a = _arenas.setdefault(device.index, _Arena())
+    need = max(a.demand, 1 << 16)
+    if (a.buf is None or a.buf.numel() < need) and not torch.cuda.is_current_stream_capturing():
+        if a.buf is not None:
+            a.retired.append(a.buf)
+        a.buf = torch.empty(need + need // 4, dtype=torch.float32, device=device)
+    a.off = a.demand = 0
+    if a.buf is not None:
+        a.buf.zero_()
+
+
+def bn_arena_end(device):
+    a = _arenas.get(device.index)
+    if a is not None:
+        a.off = -1                    # slices are handed out only inside a managed step
+
+
+def bn_totals(C_, device):
+    """A zeroed float[2C] accumulator."""
+    n = (2 * C_ + 63) // 64 * 64
+    a = _arenas.get(device.index)
+    if a is not None and a.off >= 0 and a.buf is not None:
+        a.demand += n
+        if a.off + n <= a.buf.numel():
+            out = a.buf[a.off:a.off + 2 * C_]
+            a.off += n
+            return out
+    return torch.zeros(2 * C_, dtype=torch.float32, device=device)
+
+
 def workspace(nbytes, device):
     """Grow-only scratch buffer per device, shared by all calls (the kernels that use it run on one
     stream, in order).  It is deliberately NOT keyed by stream: under CUDA-graph capture the current
@@ -99,16 +157,23 @@ def veil_from_depth(depth_nhwc):
     return veil
 
 
-def _conv_fprop(desc, x, mask, wk, bias, want_ratio, want_stats):
+def _conv_fprop(desc, x, mask, wk, bias, want_ratio, want_stats, totals=False):
     dev = x.device
     y = torch.empty((desc.N, desc.Ho, desc.Wo, desc.K), dtype=x.dtype, device=dev)
     partial = bool(desc.flags & L.CONV_PARTIAL)
     mask_out = torch.empty((desc.N, desc.Ho, desc.Wo), dtype=torch.float32, device=dev) if partial else None
     ratio = torch.empty_like(mask_out) if (partial and want_ratio) else None
-    sums = bn_partials(desc.K, dev) if want_stats else None
+    sums = None
+    if want_stats:
+        sums = bn_totals(desc.K, dev) if totals else bn_partials(desc.K, dev)
     ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 0), dev)
-    L.call("b2_pconv_fprop", C.byref(desc), L.ptr(x), L.ptr(mask), L.ptr(wk), L.ptr(bias), L.ptr(y),
-           L.ptr(mask_out), L.ptr(ratio), L.ptr(sums), L.ptr(ws), wsn, L.stream())
+    if want_stats and totals:
+        desc.flags |= L.CONV_BN_TOTALS
+    try:
+        L.call("b2_pconv_fprop", C.byref(desc), L.ptr(x), L.ptr(mask), L.ptr(wk), L.ptr(bias), L.ptr(y),
+               L.ptr(mask_out), L.ptr(ratio), L.ptr(sums), L.ptr(ws), wsn, L.stream())
+    finally:
+        desc.flags &= ~L.CONV_BN_TOTALS
     return y, mask_out, ratio, sums
 
 
@@ -228,7 +293,8 @@ class ConvBNFn(Function):
         wk = filter_krsc(weight, x.dtype, shadow)
         if partial:
             mask = mask.contiguous()
-        y, mask_out, ratio, sums = _conv_fprop(desc, x, mask if partial else None, wk, None, True, training)
+        fast = bn_totals_supported(K, x.dtype)       # totals path: no finalize kernels
+        y, mask_out, ratio, sums = _conv_fprop(desc, x, mask if partial else None, wk, None, True, training, fast)
         rows = desc.N * desc.Ho * desc.Wo
         z = torch.empty_like(y)
         mean = torch.empty(K, dtype=torch.float32, device=x.device)
@@ -236,10 +302,16 @@ class ConvBNFn(Function):
         if residual is not None:
             residual = residual.contiguous()
         row_mask = mask_out if (mask_output and partial) else None
-        L.call("b2_bn_finalize", L.ptr(sums), rows, K, L.ptr(running_mean), L.ptr(running_var), float(momentum),
-               float(eps), int(training), L.ptr(mean), L.ptr(invstd), L.stream())
-        L.call("b2_bn_apply", L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma), L.ptr(beta), L.ptr(residual),
-               L.ptr(row_mask), int(relu), L.ptr(z), rows, K, L.dt(y), L.stream())
+        if fast:
+            L.call("b2_bn_apply_totals", L.ptr(y), L.ptr(sums), rows, L.ptr(running_mean), L.ptr(running_var),
+                   float(momentum), float(eps), int(training), L.ptr(gamma), L.ptr(beta), L.ptr(residual),
+                   L.ptr(row_mask), int(relu), L.ptr(z), L.ptr(mean), L.ptr(invstd), K, L.dt(y), L.stream())
+        else:
+            L.call("b2_bn_finalize", L.ptr(sums), rows, K, L.ptr(running_mean), L.ptr(running_var), float(momentum),
+                   float(eps), int(training), L.ptr(mean), L.ptr(invstd), L.stream())
+            L.call("b2_bn_apply", L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma), L.ptr(beta), L.ptr(residual),
+                   L.ptr(row_mask), int(relu), L.ptr(z), rows, K, L.dt(y), L.stream())
+        ctx.fast = fast
         ctx.desc, ctx.relu, ctx.training, ctx.wdtype = desc, relu, training, weight.dtype
         ctx.has_res = residual is not None
         ctx.sinks = sinks
@@ -259,9 +331,6 @@ class ConvBNFn(Function):
         dev = dz.device
         K, rows = desc.K, desc.N * desc.Ho * desc.Wo
         sinks = ctx.sinks
-        parts = bn_partials(K, dev)
-        L.call("b2_bn_bwd_reduce", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
-               L.ptr(beta), L.ptr(row_mask), int(ctx.relu), L.ptr(parts), rows, K, L.dt(dz), L.stream())
         dy = torch.empty_like(y)
         dres = torch.empty_like(y) if (ctx.has_res and ctx.needs_input_grad[8]) else None
         if sinks is not None:
@@ -269,11 +338,22 @@ class ConvBNFn(Function):
         else:
             dgamma = torch.zeros(K, dtype=torch.float32, device=dev)
             dbeta = torch.zeros(K, dtype=torch.float32, device=dev)
-        gsum = torch.empty(2 * K, dtype=torch.float32, device=dev)
-        L.call("b2_bn_bwd_finalize", L.ptr(parts), K, L.ptr(gsum), L.ptr(dgamma), L.ptr(dbeta), L.stream())
-        L.call("b2_bn_bwd_apply", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
-               L.ptr(beta), L.ptr(gsum), L.ptr(row_mask), L.ptr(ratio), int(ctx.relu), int(ctx.training), L.ptr(dy),
-               L.ptr(dres), rows, K, L.dt(dz), L.stream())
+        if ctx.fast:
+            gsum = bn_totals(K, dev)
+            L.call("b2_bn_bwd_reduce_totals", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+                   L.ptr(beta), L.ptr(row_mask), int(ctx.relu), L.ptr(gsum), rows, K, L.dt(dz), L.stream())
+            L.call("b2_bn_bwd_apply_totals", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+                   L.ptr(beta), L.ptr(gsum), L.ptr(row_mask), L.ptr(ratio), int(ctx.relu), int(ctx.training),
+                   L.ptr(dy), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), rows, K, L.dt(dz), L.stream())
+        else:
+            parts = bn_partials(K, dev)
+            L.call("b2_bn_bwd_reduce", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+                   L.ptr(beta), L.ptr(row_mask), int(ctx.relu), L.ptr(parts), rows, K, L.dt(dz), L.stream())
+            gsum = torch.empty(2 * K, dtype=torch.float32, device=dev)
+            L.call("b2_bn_bwd_finalize", L.ptr(parts), K, L.ptr(gsum), L.ptr(dgamma), L.ptr(dbeta), L.stream())
+            L.call("b2_bn_bwd_apply", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+                   L.ptr(beta), L.ptr(gsum), L.ptr(row_mask), L.ptr(ratio), int(ctx.relu), int(ctx.training), L.ptr(dy),
+                   L.ptr(dres), rows, K, L.dt(dz), L.stream())
         # dy now holds dRaw = dOut * ratio -> tell the conv kernels not to scale again
         desc.flags |= L.CONV_DY_PRESCALED
         dx = dw = None

@@ -219,8 +219,12 @@ class Trainer:
     # ------------------------------------------------------------------ one optimisation step
     def _fwd_bwd(self, batch):
         self.flat.g.zero_()
-        loss, spec = self._forward_loss(*batch)
-        loss.backward()
+        ops.bn_arena_begin(self.device)          # zeroed per-channel accumulators of the totals BatchNorm path
+        try:
+            loss, spec = self._forward_loss(*batch)
+            loss.backward()
+        finally:
+            ops.bn_arena_end(self.device)
         return loss.detach(), spec
 
     def _update(self):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 2
+#define B2_ABI_VERSION 3
 
 /* slots of a BatchNorm partial-sum buffer: float[B2_BN_PARTS][2*C] (see the BatchNorm section) */
 #define B2_BN_PARTS 320
@@ -48,9 +48,11 @@ enum {
   B2_CONV_X_PREMASKED = 2,   /* caller guarantees x == x*mask_in (skip the multiply)           */
   B2_CONV_DY_PRESCALED = 4,  /* dgrad/wgrad: dy already multiplied by `ratio`                  */
   B2_CONV_FORCE_FFMA = 8,    /* debugging / fp32-accurate path even for bf16 tensors           */
-  B2_CONV_DX_ACCUMULATE = 16 /* dgrad: dx += result (bf16 TMA reduce-add) -- folds the gradient of */
+  B2_CONV_DX_ACCUMULATE = 16,/* dgrad: dx += result (bf16 TMA reduce-add) -- folds the gradient of */
                              /* a residual branch into the block input's gradient; tensor-core     */
                              /* path with stride 1 and C % 64 == 0 only, B2_E_UNSUPPORTED otherwise */
+  B2_CONV_BN_TOTALS = 32     /* fprop: bn_partials is ONE pre-zeroed float[2*K] the producer ADDS   */
+                             /* to (totals BatchNorm path, needs b2_bn_totals_supported(K, dtype))  */
 };
 
 typedef struct B2ConvDesc {
@@ -149,6 +151,30 @@ int b2_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* m
                     const float* gamma, const float* beta, const float* gsum, const float* row_mask,
                     const float* row_scale, int32_t relu, int32_t training, void* dy, void* d_residual,
                     int64_t rows, int32_t C, int32_t dtype, void* stream);
+
+/* ---- BatchNorm2d, totals path (bf16, C a power of two in [64, 2048]) --------------------
+ * Same math as above with the finalize kernels folded away: producers add their per-block sums
+ * into ONE pre-zeroed float[2*C] vector (`totals`: sum | sum of squares; `gsum`: sum g | sum g*xhat)
+ * with fp32 reductions, and the consumers derive what they need in their prologue.  Two launches
+ * per direction instead of three; the price is a run-to-run rounding difference in the last bit
+ * of the statistics (fp32 atomic order).  The caller zeroes totals / gsum (one memset per step). */
+int b2_bn_totals_supported(int32_t C, int32_t dtype);
+int b2_bn_stats_totals(const void* y, int64_t rows, int32_t C, int32_t dtype, float* totals, void* stream);
+/* training != 0: batch statistics from `totals`, running stats updated (momentum, unbiased var);
+ * training == 0: running stats (totals may be NULL).  Writes z and mean[C], invstd[C]. */
+int b2_bn_apply_totals(const void* y, const float* totals, int64_t rows, float* running_mean,
+                       float* running_var, float momentum, float eps, int32_t training, const float* gamma,
+                       const float* beta, const void* residual, const float* row_mask, int32_t relu, void* z,
+                       float* mean, float* invstd, int32_t C, int32_t dtype, void* stream);
+int b2_bn_bwd_reduce_totals(const void* dz, const void* z, const void* y, const float* mean,
+                            const float* invstd, const float* gamma, const float* beta, const float* row_mask,
+                            int32_t relu, float* gsum, int64_t rows, int32_t C, int32_t dtype, void* stream);
+/* as b2_bn_bwd_apply; additionally dgamma += gsum[C:2C], dbeta += gsum[0:C] (either may be NULL) */
+int b2_bn_bwd_apply_totals(const void* dz, const void* z, const void* y, const float* mean,
+                           const float* invstd, const float* gamma, const float* beta, const float* gsum,
+                           const float* row_mask, const float* row_scale, int32_t relu, int32_t training,
+                           void* dy, void* d_residual, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                           int32_t dtype, void* stream);
 
 /* ---- MaxPool2d(3, stride 2, pad 1) on x and veil together: partial_depthnet.py:219-220 --- */
 int b2_maxpool3x3s2_fwd(const void* x, const float* veil_in, void* y, uint8_t* argmax, float* veil_out,

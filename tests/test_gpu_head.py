@@ -147,3 +147,72 @@ def test_maxpool_with_veil(b2pose, dev, shape, dtype):
     assert torch.equal(yg.float().cpu().permute(0, 3, 1, 2), yr.detach())        # selection: exact
     assert torch.equal(vg.cpu(), vr[:, 0])
     assert rel_err(xg.grad.float().permute(0, 3, 1, 2), xr.grad) < (1e-6 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("C,rows,relu,res", [(64, 5000, 1, False), (256, 1237, 1, True), (2048, 64, 0, False)])
+def test_bn_totals_path_matches_slot_path(b2pose, dev, C, rows, relu, res):
+    """The totals BatchNorm path (fp32 reductions into one float[2C], finalize folded into the consumers)
+    against the slot path (deterministic partials + fp64 finalize kernels): statistics agree to fp32
+    rounding, outputs and gradients to one bf16 ulp."""
+    L = b2pose._lib
+    P, st = L.ptr, L.stream()
+    assert L.lib().b2_bn_totals_supported(C, L.BF16) == 1
+    assert L.lib().b2_bn_totals_supported(C, L.F32) == 0 and L.lib().b2_bn_totals_supported(48, L.BF16) == 0
+    g = torch.Generator(device="cpu").manual_seed(C + rows)
+    y = (torch.randn(rows, C, generator=g) * 1.7 + 0.3).to(dev).bfloat16()
+    dz = torch.randn(rows, C, generator=g).to(dev).bfloat16()
+    resid = torch.randn(rows, C, generator=g).to(dev).bfloat16() if res else None
+    gamma = (torch.rand(C, generator=g) + 0.5).to(dev)
+    beta = (torch.randn(C, generator=g) * 0.1).to(dev)
+    row_mask = (torch.rand(rows, generator=g) > 0.2).float().to(dev)
+    ratio = (torch.rand(rows, generator=g) + 0.5).to(dev)
+    out = {}
+    for mode in ("slots", "totals"):
+        rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        mean, invstd = torch.empty(C, device=dev), torch.empty(C, device=dev)
+        z, dy = torch.empty_like(y), torch.empty_like(y)
+        dres = torch.empty_like(y) if res else None
+        dgamma, dbeta = torch.full((C,), 2.0, device=dev), torch.full((C,), -1.0, device=dev)
+        zsave = z if (relu and res) else None
+        if mode == "slots":
+            parts = torch.empty(L.BN_PARTS * 2 * C, device=dev)
+            L.call("b2_bn_stats", P(y), rows, C, L.BF16, P(parts), st)
+            L.call("b2_bn_finalize", P(parts), rows, C, P(rm), P(rv), 0.1, 1e-5, 1, P(mean), P(invstd), st)
+            L.call("b2_bn_apply", P(y), P(mean), P(invstd), P(gamma), P(beta), P(resid), P(row_mask), relu, P(z), rows, C,
+                   L.BF16, st)
+            parts2, gsum = torch.empty(L.BN_PARTS * 2 * C, device=dev), torch.empty(2 * C, device=dev)
+            L.call("b2_bn_bwd_reduce", P(dz), P(zsave), P(y), P(mean), P(invstd), P(gamma), P(beta), P(row_mask), relu,
+                   P(parts2), rows, C, L.BF16, st)
+            L.call("b2_bn_bwd_finalize", P(parts2), C, P(gsum), P(dgamma), P(dbeta), st)
+            L.call("b2_bn_bwd_apply", P(dz), P(zsave), P(y), P(mean), P(invstd), P(gamma), P(beta), P(gsum), P(row_mask),
+                   P(ratio), relu, 1, P(dy), P(dres), rows, C, L.BF16, st)
+        else:
+            totals, gsum = torch.zeros(2 * C, device=dev), torch.zeros(2 * C, device=dev)
+            L.call("b2_bn_stats_totals", P(y), rows, C, L.BF16, P(totals), st)
+            L.call("b2_bn_apply_totals", P(y), P(totals), rows, P(rm), P(rv), 0.1, 1e-5, 1, P(gamma), P(beta), P(resid),
+                   P(row_mask), relu, P(z), P(mean), P(invstd), C, L.BF16, st)
+            L.call("b2_bn_bwd_reduce_totals", P(dz), P(zsave), P(y), P(mean), P(invstd), P(gamma), P(beta), P(row_mask),
+                   relu, P(gsum), rows, C, L.BF16, st)
+            L.call("b2_bn_bwd_apply_totals", P(dz), P(zsave), P(y), P(mean), P(invstd), P(gamma), P(beta), P(gsum),
+                   P(row_mask), P(ratio), relu, 1, P(dy), P(dres), P(dgamma), P(dbeta), rows, C, L.BF16, st)
+        torch.cuda.synchronize()
+        out[mode] = dict(mean=mean, invstd=invstd, rm=rm, rv=rv, z=z.float(), dy=dy.float(), gsum=gsum, dgamma=dgamma,
+                         dbeta=dbeta, dres=None if dres is None else dres.float())
+    a, b = out["slots"], out["totals"]
+    for k in ("mean", "invstd", "rm", "rv", "gsum", "dgamma", "dbeta"):
+        assert rel_err(b[k], a[k]) < 2e-6, k
+    for k in ("z", "dy"):
+        assert rel_err(b[k], a[k]) < 1e-2 and float((b[k] != a[k]).float().mean()) < 1e-3, k
+    if res:
+        assert torch.equal(a["dres"], b["dres"])
+    # frozen statistics (eval): running stats in, no totals
+    mean2, invstd2, z2 = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty_like(y)
+    rm, rv = a["rm"].clone(), a["rv"].clone()
+    L.call("b2_bn_apply_totals", P(y), None, rows, P(rm), P(rv), 0.1, 1e-5, 0, P(gamma), P(beta), P(resid), P(row_mask),
+           relu, P(z2), P(mean2), P(invstd2), C, L.BF16, st)
+    mean3, invstd3, z3 = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty_like(y)
+    L.call("b2_bn_finalize", None, rows, C, P(rm), P(rv), 0.1, 1e-5, 0, P(mean3), P(invstd3), st)
+    L.call("b2_bn_apply", P(y), P(mean3), P(invstd3), P(gamma), P(beta), P(resid), P(row_mask), relu, P(z3), rows, C,
+           L.BF16, st)
+    assert torch.equal(rm, a["rm"]) and torch.equal(mean2, mean3) and rel_err(invstd2, invstd3) < 1e-6
+    assert rel_err(z2.float(), z3.float()) < 1e-2
