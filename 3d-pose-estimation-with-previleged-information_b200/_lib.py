@@ -15,6 +15,7 @@ F32, BF16 = 0, 1
 CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA, CONV_DX_ACCUMULATE, CONV_BN_TOTALS = 1, 2, 4, 8, 16, 32
 ABI_VERSION = 3
 BN_PARTS = 320
+MIMIC_PARTS = 64
 
 
 class ConvDesc(C.Structure):
@@ -52,6 +53,9 @@ SIGNATURES = {
     "b2_bn_apply_totals": [_p, _p, _l, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _p],
     "b2_bn_bwd_reduce_totals": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _l, _i, _i, _p],
     "b2_bn_bwd_apply_totals": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p],
+    "b2_mimic_loss_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "b2_mimic_loss_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
+    "b2_attention_map": [_p, _i, _i, _i, _i, _p, _p],
     "b2_maxpool3x3s2_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2_maxpool3x3s2_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2_head_fwd": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],

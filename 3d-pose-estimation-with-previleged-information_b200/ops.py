@@ -530,6 +530,65 @@ class PoseLossFn(Function):
         return dcoords * dloss, None, None, None, None, None
 
 
+MIMIC_MODES = {"l2": 0, "sigmoid": 1, "bce": 2}
+
+
+class MimicLossFn(Function):
+    """Feature-mimic loss of the distillation step (Trainer.distill, depth_train.py:115-129).
+
+    forward(teach_last, last_feat, atten_map, mode) -> 0-dim fp32 loss; gradient flows to last_feat only
+    (the teacher runs under no_grad, depth_train.py:194-195)."""
+
+    @staticmethod
+    def forward(ctx, teach, student, atten, mode):
+        L.require_cuda(teach, student, atten)
+        if teach.shape != student.shape or teach.dim() != 4:
+            raise ValueError("teacher / student features must be [N, C, H, W] of one shape, got %s and %s"
+                             % (tuple(teach.shape), tuple(student.shape)))
+        N, Cc, H, W = student.shape
+        if atten.numel() != N * H * W:
+            raise ValueError("attention map must hold N*H*W = %d values, got %s" % (N * H * W, tuple(atten.shape)))
+        student, layout = _logit_layout(student)
+        teach = teach.detach().to(student.dtype)
+        if layout == 0:
+            if not teach.permute(0, 2, 3, 1).is_contiguous():
+                teach = teach.contiguous(memory_format=torch.channels_last)
+        else:
+            teach = teach.contiguous()
+        atten = atten.detach().float().contiguous()
+        dev = student.device
+        partials = torch.empty(N * L.MIMIC_PARTS, dtype=torch.float32, device=dev)
+        scale = torch.empty(N, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        L.call("b2_mimic_loss_fwd", L.ptr(teach), L.ptr(student), L.ptr(atten), N, Cc, H * W, layout, L.dt(student),
+               int(mode), L.ptr(partials), L.ptr(scale), L.ptr(loss), L.stream())
+        ctx.cfg = (N, Cc, H * W, layout, int(mode))
+        ctx.save_for_backward(teach, student, atten, scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        teach, student, atten, scale = ctx.saved_tensors
+        N, Cc, HW, layout, mode = ctx.cfg
+        dloss = dloss.float().contiguous()
+        ds = torch.empty_like(student)
+        L.call("b2_mimic_loss_bwd", L.ptr(teach), L.ptr(student), L.ptr(atten), L.ptr(scale), L.ptr(dloss), N, Cc, HW,
+               layout, L.dt(student), mode, L.ptr(ds), L.stream())
+        return None, ds, None, None
+
+
+def attention_map(image_coords, side_in, side_out):
+    """utils.get_attention on device: image_coords [N, J, 2] (x, y) -> [N, 1, side_out, side_out] fp32."""
+    L.require_cuda(image_coords)
+    c = image_coords.detach().float().contiguous()
+    N, J, two = c.shape
+    if two != 2:
+        raise ValueError("image_coords must be [N, J, 2]")
+    out = torch.empty((N, 1, side_out, side_out), dtype=torch.float32, device=c.device)
+    L.call("b2_attention_map", L.ptr(c), N, J, int(side_in), int(side_out), L.ptr(out), L.stream())
+    return out
+
+
 def unproject_depth(img, intrinsic):
     """utils.to_depth on device: img [..., H, W] fp32 CUDA tensor, intrinsic 3x3 (host array-like)."""
     import numpy as np

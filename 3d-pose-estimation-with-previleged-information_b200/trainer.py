@@ -34,7 +34,8 @@ def train_args(**kw):
                 partial_conv=False, pretrain=False, early_dist=False, skip_relu=False, extra_channel=False,
                 joint_space=False, warmup=1, n_epochs=20, batch_size=64, side_in=257, stride=16, num_joints=19,
                 depth=16, warmup_factor=0.2, learn_rate=5e-5, learn_decay=0.2, grad_norm=5.0, grad_scaling=32.0,
-                weight_decay=4e-5, depth_range=1000.0, loss_div=10.0, criterion="SmoothL1")
+                weight_decay=4e-5, depth_range=1000.0, loss_div=10.0, criterion="SmoothL1", semi_teach=False,
+                sigmoid=False, bin_dist=False, do_freeze=False, alpha_init=0.1, alpha_dest=0.1, alpha_span=10)
     base.update(kw)
     return SimpleNamespace(**base)
 
@@ -120,8 +121,17 @@ class Trainer:
         self.half_acc = bool(g("half_acc", False))
         self.depth_only = bool(g("depth_only", True))
         self.do_fusion = bool(g("do_fusion", False))
-        if g("do_teach", False) or g("semi_teach", False):
-            raise NotImplementedError("distillation / semi-supervised steps are outside this hot path")
+        if g("semi_teach", False):
+            raise NotImplementedError("semi_teach needs the reference's private data loaders; pass the unlabelled "
+                                      "batch to train_step(batch, semi_batch=...) instead")
+        # distillation ("privileged information") step: depth_train.py:52-56,97-99
+        self.do_teach = bool(g("do_teach", False))
+        self.sigmoid, self.bin_dist = bool(g("sigmoid", False)), bool(g("bin_dist", False))
+        self.do_freeze = bool(g("do_freeze", False))
+        self.alpha_init, self.alpha_dest = g("alpha_init", 0.1), g("alpha_dest", 0.1)
+        self.alpha_span = g("alpha_span", 10)
+        self.alpha = float(self.alpha_init)
+        self.teacher = None
         self.depth, self.num_joints = args.depth, args.num_joints
         self.side_in, self.stride = args.side_in, args.stride
         self.depth_range = g("depth_range", 1000.0)
@@ -161,6 +171,8 @@ class Trainer:
         self.launches_per_step = 0
         self._graphs = {}
         self._static = {}
+        self._static_semi = {}
+        self._extras = {}
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -192,6 +204,43 @@ class Trainer:
     def to(self, image, device):
         return image.to(device, non_blocking=True)      # the bf16 cast happens on device (ops.to_nhwc)
 
+    # ------------------------------------------------------------------ distillation (depth_train.py:107-129,156-283)
+    def set_teacher(self, teacher):
+        """depth_train.py:107-108.  The teacher only ever runs under no_grad (:194-195)."""
+        if next(teacher.parameters()).device != self.device:
+            raise RuntimeError("the teacher must live on the trainer's device (%s)" % self.device)
+        self.teacher = teacher.half() if self.half_acc else teacher
+        for p in self.teacher.parameters():
+            p.requires_grad_(False)
+        self._graphs.clear()                              # captured steps do not contain the teacher
+
+    def get_dist_weight(self, epoch):
+        """depth_train.py:641-647."""
+        import numpy as np
+        alphas = np.linspace(self.alpha_init, self.alpha_dest, self.alpha_span)
+        return float(alphas[epoch - 1]) if epoch - 1 < self.alpha_span else float(self.alpha_dest)
+
+    def freeze_batchnorm(self):
+        """depth_train.py:156-158."""
+        self.teacher.eval()
+        self.model.freeze_batchnorm()
+
+    def teach_infer(self, color_image, depth_image):
+        """depth_train.py:682-691."""
+        if getattr(self.teacher, "fused", False) or self.do_fusion:
+            return self.teacher(color_image, depth_image)
+        return self.teacher(depth_image if self.depth_only else color_image)
+
+    def distill(self, batch, teach_last, last_feat, atten_map):
+        """depth_train.py:115-129 as one fused reduction (+ one backward pass)."""
+        return utils.mimic_loss(teach_last, last_feat, atten_map, sigmoid=self.sigmoid, bin_dist=self.bin_dist)
+
+    def _distill_forward(self, color, depth, atten):
+        with torch.no_grad():
+            _, teach_last = self.teach_infer(color, depth)
+        cam_feat, last_feat = self.vanilla_infer(color, 0, True)       # the student always sees the colour image (:197)
+        return cam_feat, self.distill(color.size(0), teach_last, last_feat, atten)
+
     # ------------------------------------------------------------------ forward pieces
     def vanilla_infer(self, in_image, i_batch=0, ret_last=False):
         out = self.model(in_image)
@@ -204,7 +253,22 @@ class Trainer:
         cam_feat, last_feat = self.model(color_image, depth_image)
         return (cam_feat, last_feat) if ret_last else cam_feat
 
-    def _forward_loss(self, color, depth, true_cam, true_val):
+    def _forward_loss(self, color, depth, true_cam, true_val, atten=None, semi=None):
+        self._extras = {}
+        if atten is not None:
+            if self.teacher is None:
+                raise RuntimeError("a 5-tuple batch (with an attention map) needs set_teacher() first")
+            cam_feat, dist_loss = self._distill_forward(color, depth, atten)
+            coords = utils.heatmap_coords(cam_feat, self.depth, self.num_joints, self.depth_range)
+            cam_loss, spec = utils.pose_loss(coords, true_cam, true_val, self.key_index, self.loss_div, self.criterion)
+            alpha = self.hyper[3]                      # device scalar: the schedule moves without re-capture
+            loss = dist_loss * alpha + cam_loss        # depth_train.py:219
+            self._extras = dict(cam_loss=cam_loss.detach(), dist_loss=dist_loss.detach())
+            if semi is not None:                       # semi_train, depth_train.py:132-153,221-229
+                _, semi_loss = self._distill_forward(semi[0], semi[1], semi[-1])
+                loss = loss + semi_loss * alpha
+                self._extras["semi_dist_loss"] = semi_loss.detach()
+            return loss, spec
         if self.do_fusion or getattr(self.model, "fused", False):
             cam_feat = self.fusion_infer(color, depth)
         else:
@@ -217,11 +281,14 @@ class Trainer:
         return loss, spec
 
     # ------------------------------------------------------------------ one optimisation step
-    def _fwd_bwd(self, batch):
+    def _fwd_bwd(self, batch, semi=None):
         self.flat.g.zero_()
         ops.bn_arena_begin(self.device)          # zeroed per-channel accumulators of the totals BatchNorm path
         try:
-            loss, spec = self._forward_loss(*batch)
+            if semi is not None:
+                loss, spec = self._forward_loss(*batch, semi=semi)
+            else:
+                loss, spec = self._forward_loss(*batch)
             loss.backward()
         finally:
             ops.bn_arena_end(self.device)
@@ -245,6 +312,7 @@ class Trainer:
         host[0] = self.lr
         host[1] = 1.0 - self.betas[0] ** t
         host[2] = math.sqrt(1.0 - self.betas[1] ** t)
+        host[3] = self.alpha
         self.hyper.copy_(host, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -295,15 +363,31 @@ class Trainer:
             s.copy_(t.view(torch.uint8) if t.dtype == torch.bool else t, non_blocking=True)
         return key, st
 
-    def train_step(self, batch):
+    def train_step(self, batch, semi_batch=None):
         """One fwd + bwd + clip + Adam step on ``batch`` = (color, depth, true_cam, true_val)
-        (host or device tensors).  Returns dict(loss=0-dim tensor, spec_cam=[N,J,3], grad_norm)."""
+        (host or device tensors).  Returns dict(loss=0-dim tensor, spec_cam=[N,J,3], grad_sumsq).
+
+        With a teacher set (``set_teacher``) and a 5-tuple batch (..., atten_map) this is the distillation
+        step of depth_train.py:179-283: loss = dist_loss * alpha + cam_loss; the dict then also carries
+        ``cam_loss`` and ``dist_loss`` (``loss`` is the total).  ``semi_batch`` = an unlabelled 5-tuple whose
+        mimic term is added (semi_train, :132-153)."""
         self._set_hyper()
         key, st = self._static_batch(batch)
+        st_semi = None
+        if semi_batch is not None:
+            if len(batch) != 5 or len(semi_batch) != 5:
+                raise ValueError("semi_batch needs the distillation 5-tuples (color, depth, true_cam, true_val, atten_map)")
+            self._static, keep = self._static_semi, self._static          # separate static buffers
+            try:
+                key2, st_semi = self._static_batch(semi_batch)
+            finally:
+                self._static_semi, self._static = self._static, keep
+            key = (key, key2)
         dist_on = self.world > 1
         n0 = L.launches
         if not self.use_graph:
-            loss, spec = self._fwd_bwd(st)
+            loss, spec = self._fwd_bwd(st, st_semi)
+            extras = self._extras
             if dist_on:
                 self.buckets.allreduce()
             self._update()
@@ -313,39 +397,42 @@ class Trainer:
             if entry is None:
                 entry = self._capture(key, st)
             if entry["stage"] < 3:               # eager warm-up iterations before capture
-                loss, spec = self._fwd_bwd(st)
+                loss, spec = self._fwd_bwd(st, st_semi)
+                extras = self._extras
                 if dist_on:
                     self.buckets.allreduce()
                 self._update()
                 entry["stage"] += 1
                 if entry["stage"] == 3:
-                    self._do_capture(entry, st)
+                    self._do_capture(entry, st, st_semi)
             else:
                 entry["fb"].replay()
                 if dist_on:
                     self.buckets.allreduce()
                 entry["up"].replay()
-                loss, spec = entry["loss"], entry["spec"]
+                loss, spec, extras = entry["loss"], entry["spec"], entry["extras"]
         if self.bns and self.model.training:
-            torch._foreach_add_([m.num_batches_tracked for m in self.bns if m.training], 1)
-        return dict(loss=loss, spec_cam=spec, grad_sumsq=self.sumsq)
+            live = [m.num_batches_tracked for m in self.bns if m.training]      # none after freeze_batchnorm()
+            if live:
+                torch._foreach_add_(live, 1)
+        return dict(loss=loss, spec_cam=spec, grad_sumsq=self.sumsq, **extras)
 
     def _capture(self, key, st):
         entry = dict(stage=0)
         self._graphs[key] = entry
         return entry
 
-    def _do_capture(self, entry, st):
+    def _do_capture(self, entry, st, st_semi=None):
         torch.cuda.synchronize()
         pool = torch.cuda.graph_pool_handle()
         n0 = L.launches
         fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(fb, pool=pool):
-            loss, spec = self._fwd_bwd(st)
+            loss, spec = self._fwd_bwd(st, st_semi)
         up = torch.cuda.CUDAGraph()
         with torch.cuda.graph(up, pool=pool):
             self._update()
-        entry.update(fb=fb, up=up, loss=loss, spec=spec)
+        entry.update(fb=fb, up=up, loss=loss, spec=spec, extras=self._extras)
         self.launches_per_step = L.launches - n0     # libb2pose kernels recorded into the two graphs
         # the capture itself did not execute: the grads in the flat buffer are from the last eager
         # warm-up step and have been consumed already, nothing to redo.
@@ -373,6 +460,43 @@ class Trainer:
         print("\n=> train Epoch[%d]  Cam Loss: %1.4f\n" % (epoch, loss_avg))
         return dict(cam_train_loss=loss_avg)
 
+    def distill_train(self, epoch, data_loader, device=None, semi_loader=None):
+        """depth_train.py:161-283: data_loader yields (color, depth, true_cam, true_val, atten_map)."""
+        if self.teacher is None:
+            raise RuntimeError("distill_train needs set_teacher() first")
+        if self.do_freeze:
+            self.freeze_batchnorm()
+        self.alpha = self.get_dist_weight(epoch)
+        print("\n=> alpha value: {:.2f}".format(self.alpha))
+        n_batches = len(data_loader)
+        cam_sum = dist_sum = 0.0
+        cam_n = dist_n = 0
+        semi_it = iter(semi_loader) if semi_loader is not None else None
+        for i_batch, batch in enumerate(data_loader):
+            semi = None
+            if semi_it is not None:
+                semi = next(semi_it, None)
+                if semi is None:                         # depth_train.py:133-138: restart the semi worker
+                    semi_it = iter(semi_loader)
+                    semi = next(semi_it)
+            out = self.train_step(tuple(batch), None if semi is None else tuple(semi))
+            n = batch[2].size(0)
+            cam, dist = out["cam_loss"].item(), out["dist_loss"].item()
+            cam_sum, cam_n = cam_sum + cam * n, cam_n + n
+            dist_sum, dist_n = dist_sum + dist * n, dist_n + n
+            msg = "[=] train Epoch[{0}] Batch[{1}|{2}] ".format(epoch, i_batch, n_batches)
+            msg += " Cam Loss {:.4f} ".format(cam) + " Dist Loss {:.4f} ".format(dist)
+            if semi is not None:
+                sn = semi[2].size(0)
+                sd = out["semi_dist_loss"].item()
+                dist_sum, dist_n = dist_sum + sd * sn, dist_n + sn
+                msg += " Semi Loss {:.4f}".format(sd)
+            print(msg, flush=True)
+        cam_sum /= max(cam_n, 1)
+        dist_sum /= max(dist_n, 1)
+        print("\n=> train Epoch[%d]  Cam Loss: %1.4f  Dist Loss: %1.4f\n\n" % (epoch, cam_sum, dist_sum))
+        return dict(dist_train_loss=dist_sum, cam_train_loss=cam_sum)
+
     def vanilla_train(self, epoch, data_loader, device=None):
         return self._epoch(epoch, data_loader, device)
 
@@ -384,6 +508,8 @@ class Trainer:
     def train(self, epoch, data_loader):
         self.model.train()
         self.adapt_learn_rate(epoch)
+        if self.do_teach:
+            return self.distill_train(epoch, data_loader, self.device)
         if self.do_fusion:
             return self.fusion_train(epoch, data_loader, self.device)
         return self.vanilla_train(epoch, data_loader, self.device)

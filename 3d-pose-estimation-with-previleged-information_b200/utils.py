@@ -29,6 +29,29 @@ def pose_loss(coords, true_cam, true_val, key_index, loss_div=10.0, criterion="S
     return ops.PoseLossFn.apply(coords, true_cam, true_val, key_index, loss_div, criterion)
 
 
+def mimic_loss(teach_last, last_feat, atten_map, sigmoid=False, bin_dist=False):
+    """Trainer.distill (depth_train.py:115-129): the feature-mimic term of the distillation step.
+    ``bin_dist`` selects the BCE variant (:117-121), ``sigmoid`` the squashed L2 (:123), default the
+    attention-weighted L2 norm per sample, averaged over the batch."""
+    mode = ops.MIMIC_MODES["bce" if bin_dist else ("sigmoid" if sigmoid else "l2")]
+    return ops.MimicLossFn.apply(teach_last, last_feat, atten_map, mode)
+
+
+def get_attention(side_in, stride, image_coords, attention):
+    """utils.get_attention (utils.py:14-42).  image_coords: (J, 2) numpy array -> numpy (1, S', S') like the
+    reference (computed on the GPU); a CUDA tensor [N, J, 2] -> CUDA tensor [N, 1, S', S']."""
+    side_out = (side_in - 1) // stride + 1
+    if torch.is_tensor(image_coords) and image_coords.is_cuda:
+        if not attention:
+            return torch.ones((image_coords.shape[0], 1, side_out, side_out), device=image_coords.device)
+        return ops.attention_map(image_coords, side_in, side_out)
+    if not attention:
+        return np.ones((1, side_out, side_out))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    c = torch.as_tensor(np.ascontiguousarray(image_coords, np.float32)).to(dev)[None]
+    return ops.attention_map(c, side_in, side_out)[0].cpu().numpy().astype(np.float64)
+
+
 def to_depth(image, depth_cam):
     """Ray length -> z-depth, ``image / sqrt(|image_to_camera(u, v)|^2 + 1)`` (utils.py:68-75 with
     cameralib.Camera.image_to_camera, no-distortion branch cameralib.py:192-194).

@@ -176,6 +176,26 @@ int b2_bn_bwd_apply_totals(const void* dz, const void* z, const void* y, const f
                            void* dy, void* d_residual, float* dgamma, float* dbeta, int64_t rows, int32_t C,
                            int32_t dtype, void* stream);
 
+/* ---- feature-mimic (distillation) loss -------------------------------------------------
+ * replaces Trainer.distill, depth_train.py:115-129 (the "privileged information" term):
+ *   mode 0: mean_n || (t - s) * a ||_2     mode 1: mean_n || (sigmoid(t) - sigmoid(s)) * a ||_2
+ *   mode 2: mean_all(BCEWithLogits(s, sigmoid(t))) * sum(a) / N          (bin_dist, as written there)
+ * teach / student: [N, C, H, W] logical, layout 0 = NHWC memory, 1 = NCHW memory, dtype fp32 | bf16;
+ * atten: [N, H*W] fp32.  partials: float[N * B2_MIMIC_PARTS] scratch, scale: float[N] (saved for the
+ * backward), loss: one float.  Backward: dstudent = dloss[0] * d(loss)/d(student)  (dloss device
+ * pointer or NULL = 1). */
+#define B2_MIMIC_PARTS 64
+int b2_mimic_loss_fwd(const void* teach, const void* student, const float* atten, int32_t N, int32_t C,
+                      int32_t HW, int32_t layout, int32_t dtype, int32_t mode, float* partials, float* scale,
+                      float* loss, void* stream);
+int b2_mimic_loss_bwd(const void* teach, const void* student, const float* atten, const float* scale,
+                      const float* dloss, int32_t N, int32_t C, int32_t HW, int32_t layout, int32_t dtype,
+                      int32_t mode, void* dstudent, void* stream);
+/* utils.get_attention, utils.py:14-42: out[n, y, x] = sum_j exp(-|(x, y) - coords[n, j] * side_out / side_in|^2 / 5),
+ * divided by its maximum.  image_coords: [N, J, 2] fp32 (x, y) pixels of the side_in image; out: [N, side_out^2]. */
+int b2_attention_map(const float* image_coords, int32_t N, int32_t J, int32_t side_in, int32_t side_out,
+                     float* out, void* stream);
+
 /* ---- MaxPool2d(3, stride 2, pad 1) on x and veil together: partial_depthnet.py:219-220 --- */
 int b2_maxpool3x3s2_fwd(const void* x, const float* veil_in, void* y, uint8_t* argmax, float* veil_out,
                         int32_t N, int32_t H, int32_t W, int32_t C, int32_t dtype, void* stream);

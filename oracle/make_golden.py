@@ -292,6 +292,103 @@ def gen_nets(ref):
     return out
 
 
+# ------------------------------------------------------------------ distillation step
+DISTILL_CASES = [
+    # tag, teacher kind, teacher extra, student extra, distill kwargs
+    ("dist_pf18_l2",      "partial_fusionnet", {}, dict(depth_only=False), dict()),
+    ("dist_f18skip_sig",  "fusionnet", dict(skip_relu=True, early_dist=True),
+     dict(depth_only=False, skip_relu=True, early_dist=True), dict(sigmoid=True)),
+    ("dist_pf18_bce_frz", "partial_fusionnet", {}, dict(depth_only=False), dict(bin_dist=True, freeze=True)),
+]
+
+
+def gen_distill(ref):
+    import depth_train                      # noqa: imports cleanly; only Trainer.__init__ needs the private paths
+    DT = depth_train.Trainer
+    U = ref["utils"]
+    out = {}
+    # -- the loss alone (Trainer.distill called unbound on a namespace carrying the two switches)
+    g = torch.Generator().manual_seed(5)
+    names = []
+    for name, (N, C, H, W) in (("small", (3, 16, 5, 5)), ("odd", (2, 6, 3, 4))):
+        t = torch.randn(N, C, H, W, generator=g) * 2
+        a = torch.rand(N, 1, H, W, generator=g)
+        for mode, kw in (("l2", dict(sigmoid=False, bin_dist=False)), ("sigmoid", dict(sigmoid=True, bin_dist=False)),
+                         ("bce", dict(sigmoid=False, bin_dist=True))):
+            sfeat = (torch.randn(N, C, H, W, generator=g) * 2).requires_grad_(True)
+            loss = DT.distill(types.SimpleNamespace(**kw), N, t, sfeat, a)
+            loss.backward()
+            key = f"loss_{name}_{mode}"
+            out.update({key + "_t": np_(t), key + "_s": np_(sfeat), key + "_a": np_(a),
+                        key + "_loss": np.array(float(loss), np.float64), key + "_ds": np_(sfeat.grad)})
+            assert abs(float(po.distill_loss(t, sfeat.detach(), a, **kw)) - float(loss)) < 1e-6 * max(1, abs(float(loss)))
+            names.append(key)
+    out["loss_names"] = np.array(names)
+    # -- attention maps
+    for name, (side, stride, J) in (("att_257", (257, 16, 17)), ("att_64", (64, 16, 5)), ("att_48s8", (48, 8, 3))):
+        coords = (torch.rand(J, 2, generator=g) * side).numpy().astype(np.float64)
+        out[name + "_coords"] = coords
+        out[name + "_cfg"] = np.array([side, stride], np.int32)
+        out[name + "_map"] = U.get_attention(side, stride, coords, True)
+        out[name + "_ones"] = U.get_attention(side, stride, coords, False)
+    # -- schedule
+    sched = types.SimpleNamespace(alpha_init=0.5, alpha_dest=0.1, alpha_span=5)
+    out["alpha_sched"] = np.array([DT.get_dist_weight(sched, e) for e in range(1, 9)], np.float64)
+    # -- whole steps: distill_train core (depth_train.py:179-283, non-half branch) around the imported nets
+    tags = []
+    for tag, tkind, textra, sextra, dkw in DISTILL_CASES:
+        side, N, J, model = 64, 2, 17, "resnet18"
+        tcfg = po.net_config(side_in=side, num_joints=J, **textra)
+        scfg = po.net_config(side_in=side, num_joints=J, **sextra)
+        teacher = build_reference_net(ref, tkind, model, tcfg)
+        teacher.load_state_dict(po.init_state(tkind, model, tcfg, seed=21))
+        student = build_reference_net(ref, "depthnet", model, scfg)
+        student.load_state_dict(po.init_state("depthnet", model, scfg, seed=11))
+        teacher.train()
+        student.train()
+        freeze = dkw.get("freeze", False)
+        if freeze:                                            # Trainer.freeze_batchnorm, depth_train.py:156-158
+            teacher.eval()
+            student.freeze_batchnorm()
+        ns = types.SimpleNamespace(sigmoid=dkw.get("sigmoid", False), bin_dist=dkw.get("bin_dist", False))
+        opt = torch.optim.Adam(list(student.parameters()), 5e-5, weight_decay=4e-5)
+        batch = po.synth_distill_batch(N, side, J, stride=16, seed=3)
+        color, depth, true_cam, true_val, atten, _ = batch
+        alpha, key_index, side_out = 0.3, J - 1, (side - 1) // 16 + 1
+        cams, dists, gns = [], [], []
+        for it in range(2):
+            with torch.no_grad():
+                _, teach_last = teacher(color, depth)
+            cam_feat, last_feat = student(color)
+            dist_loss = DT.distill(ns, N, teach_last, last_feat, atten)
+            heat = U.to_heatmap(cam_feat, scfg.depth, J, side_out, side_out)
+            rel = U.decode(heat, 1000.0)
+            rel = rel - rel[:, key_index:key_index + 1]
+            spec = rel + true_cam[:, key_index:key_index + 1]
+            sel = true_val.view(-1)
+            cam_loss = nn.SmoothL1Loss(reduction="mean")(spec.view(-1, 3)[sel] / 10.0, true_cam.view(-1, 3)[sel] / 10.0)
+            loss = dist_loss * alpha + cam_loss
+            opt.zero_grad()
+            loss.backward()
+            gn = nn.utils.clip_grad_norm_(list(student.parameters()), 5.0)
+            if it == 0:
+                out[f"{tag}_spec"] = np_(spec)
+                out[f"{tag}_last_slice"] = np_(last_feat[:, :8])
+                out[f"{tag}_teach_slice"] = np_(teach_last[:, :8])
+                out[f"{tag}_g_l4"] = np_(dict(student.named_parameters())["layer4.1.conv2.weight"].grad.reshape(-1)[:64])
+                out[f"{tag}_gn_l1"] = np.array(float(dict(student.named_parameters())["layer1.0.conv1.weight"].grad.norm()))
+            opt.step()
+            cams.append(float(cam_loss)); dists.append(float(dist_loss)); gns.append(float(gn))
+        out[f"{tag}_cam"] = np.array(cams, np.float64)
+        out[f"{tag}_dist"] = np.array(dists, np.float64)
+        out[f"{tag}_gn"] = np.array(gns, np.float64)
+        out[f"{tag}_teacher_bn1_rm"] = np_(teacher.state_dict()["bn1.running_mean"])
+        tags.append(tag)
+        print(tag, "cam", cams, "dist", dists, "gn", gns, flush=True)
+    out["tags"] = np.array(tags)
+    return out
+
+
 def gen_shapes(ref):
     """KA7: parameter counts and output shapes of the full-size nets (no forward needed for counts)."""
     out = {}
@@ -307,9 +404,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ref = import_reference()
-    which = sys.argv[1:] or ["ka", "pconv", "head", "to_depth", "shapes", "nets"]
+    which = sys.argv[1:] or ["ka", "pconv", "head", "to_depth", "shapes", "nets", "distill"]
     table = dict(ka=gen_known_answers, pconv=gen_pconv_cases, head=gen_head, to_depth=gen_to_depth,
-                 shapes=gen_shapes, nets=gen_nets)
+                 shapes=gen_shapes, nets=gen_nets, distill=gen_distill)
     for name in which:
         data = table[name](ref)
         path = os.path.join(OUT, f"{name}.npz")

@@ -480,6 +480,83 @@ class StepOracle:
         return float(loss), float(gn), spec.detach(), z.detach()
 
 
+# ----------------------------------------------------------------------------
+# distillation ("privileged information") step
+# ----------------------------------------------------------------------------
+
+
+def distill_loss(teach_last, last_feat, atten_map, sigmoid=False, bin_dist=False):
+    """Trainer.distill, depth_train.py:115-129 (restated; `batch` there is last_feat.size(0))."""
+    batch = last_feat.size(0)
+    if bin_dist:
+        diff = F.binary_cross_entropy_with_logits(last_feat, torch.sigmoid(teach_last))     # :117 (a scalar mean)
+        diff = torch.mul(diff, atten_map)                                                     # :119
+        return torch.sum(diff.view(batch, -1), dim=-1).mean()                                 # :121
+    diff = (torch.sigmoid(teach_last) - torch.sigmoid(last_feat)) if sigmoid else (teach_last - last_feat)   # :123
+    diff = torch.mul(diff, atten_map)                                                         # :125
+    return torch.linalg.norm(diff.view(batch, -1), dim=-1).mean()                             # :127
+
+
+def get_attention(side_in, stride, image_coords, attention=True):
+    """utils.get_attention, utils.py:14-42 (numpy, float64)."""
+    side_out = (side_in - 1) // stride + 1
+    if not attention:
+        return np.ones((side_out, side_out))[None]
+    cx, cy = np.meshgrid(np.arange(side_out), np.arange(side_out))
+    cx, cy = cx[..., None], cy[..., None]
+    dist_x = cx - image_coords[:, 0] / (side_in / side_out)
+    dist_y = cy - image_coords[:, 1] / (side_in / side_out)
+    radial = np.exp(-(dist_x ** 2 + dist_y ** 2) / 5.0).sum(axis=-1)
+    return (radial / np.amax(radial))[None]
+
+
+def dist_weight_at(epoch, alpha_init=0.1, alpha_dest=0.1, alpha_span=10):
+    """Trainer.get_dist_weight, depth_train.py:641-647."""
+    alphas = np.linspace(alpha_init, alpha_dest, alpha_span)
+    return float(alphas[epoch - 1]) if epoch - 1 < alpha_span else float(alpha_dest)
+
+
+def synth_distill_batch(n, side, num_joints, stride=16, seed=1, invalid_frac=0.25):
+    """synth_batch + the attention map the data set attaches (depth_datasets.py builds it with
+    utils.get_attention from the projected joints): joints ~ U(0, side) pixels."""
+    color, depth, true_cam, true_val = synth_batch(n, side, num_joints, seed, invalid_frac)
+    g = torch.Generator().manual_seed(seed + 1000)
+    coords = torch.rand(n, num_joints, 2, generator=g) * side
+    atten = np.stack([get_attention(side, stride, coords[i].numpy().astype(np.float64)) for i in range(n)])
+    return color, depth, true_cam, true_val, torch.tensor(atten, dtype=torch.float32), coords
+
+
+class DistillOracle(StepOracle):
+    """distill_train core, depth_train.py:179-283 (non-half branch): a fixed teacher (train-mode BN under
+    no_grad unless `freeze`), the student sees the colour image, loss = dist * alpha + cam."""
+
+    def __init__(self, sd, kind, model, cfg, teacher_sd, teacher_kind, teacher_cfg, *, sigmoid=False, bin_dist=False,
+                 freeze=False, **kw):
+        super().__init__(sd, kind, model, cfg, **kw)
+        self.tsd, self.tkind, self.tcfg = teacher_sd, teacher_kind, teacher_cfg
+        self.sigmoid, self.bin_dist, self.freeze = sigmoid, bin_dist, freeze
+
+    def step(self, batch, alpha):
+        color, depth, true_cam, true_val, atten = batch[:5]
+        with torch.no_grad():
+            if self.tkind in ("fusionnet", "partial_fusionnet"):
+                _, teach_last = net_forward(self.tsd, self.tkind, self.model, self.tcfg, color, depth, not self.freeze)
+            else:
+                _, teach_last = net_forward(self.tsd, self.tkind, self.model, self.tcfg,
+                                            depth if self.tcfg.depth_only else color, None, not self.freeze)
+        z, last = net_forward(self.sd, self.kind, self.model, self.cfg, color, None, not self.freeze)
+        dist = distill_loss(teach_last, last, atten, self.sigmoid, self.bin_dist)
+        cam, spec = pose_loss(z, true_cam, true_val, depth=self.cfg.depth, num_joints=self.cfg.num_joints,
+                              side_out=self.side_out, depth_range=self.depth_range, key_index=self.key_index,
+                              loss_div=self.loss_div, criterion=self.criterion)
+        loss = dist * alpha + cam
+        self.opt.zero_grad()
+        loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_([self.sd[k] for k in self.names], self.grad_norm)
+        self.opt.step()
+        return float(cam), float(dist), float(gn), spec.detach(), last.detach()
+
+
 def learn_rate_at(epoch, *, learn_rate=5e-5, warmup=1, warmup_factor=0.2, learn_decay=0.2):
     """depth_train.py:621-638."""
     e = epoch - 1

@@ -152,3 +152,55 @@ def test_net_and_step(golden_dir, tag):
     np.testing.assert_allclose(sd["conv1.weight"].detach().reshape(-1)[:64].numpy(), g[f"{tag}_conv1_after"],
                                rtol=1e-3, atol=2e-5)
     assert sum(sd[k].numel() for k in po.trainable_names(sd)) == int(g[f"{tag}_nparams"])
+
+
+# ------------------------------------------------------------------ distillation step
+DISTILL_CASES = {
+    "dist_pf18_l2": ("partial_fusionnet", {}, dict(depth_only=False), dict()),
+    "dist_f18skip_sig": ("fusionnet", dict(skip_relu=True, early_dist=True),
+                         dict(depth_only=False, skip_relu=True, early_dist=True), dict(sigmoid=True)),
+    "dist_pf18_bce_frz": ("partial_fusionnet", {}, dict(depth_only=False), dict(bin_dist=True, freeze=True)),
+}
+MIMIC_KW = {"l2": dict(sigmoid=False, bin_dist=False), "sigmoid": dict(sigmoid=True, bin_dist=False),
+            "bce": dict(sigmoid=False, bin_dist=True)}
+
+
+def test_distill_loss_attention_schedule(golden_dir):
+    g = load(golden_dir, "distill")
+    for key in g["loss_names"]:
+        mode = str(key).rsplit("_", 1)[1]
+        s = torch.tensor(g[f"{key}_s"], requires_grad=True)
+        loss = po.distill_loss(torch.tensor(g[f"{key}_t"]), s, torch.tensor(g[f"{key}_a"]), **MIMIC_KW[mode])
+        loss.backward()
+        np.testing.assert_allclose(float(loss), float(g[f"{key}_loss"]), rtol=1e-6)
+        assert rel_err(s.grad, g[f"{key}_ds"]) < 1e-5, key
+    for name in ("att_257", "att_64", "att_48s8"):
+        side, stride = (int(v) for v in g[name + "_cfg"])
+        np.testing.assert_allclose(po.get_attention(side, stride, g[name + "_coords"], True), g[name + "_map"], rtol=1e-12)
+        assert np.array_equal(po.get_attention(side, stride, g[name + "_coords"], False), g[name + "_ones"])
+        assert g[name + "_map"].shape == (1, (side - 1) // stride + 1, (side - 1) // stride + 1)
+        assert g[name + "_map"].max() == 1.0
+    sched = [po.dist_weight_at(e, 0.5, 0.1, 5) for e in range(1, 9)]
+    np.testing.assert_allclose(sched, g["alpha_sched"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("tag", sorted(DISTILL_CASES))
+def test_distill_step(golden_dir, tag):
+    g = load(golden_dir, "distill")
+    tkind, textra, sextra, dkw = DISTILL_CASES[tag]
+    tcfg = po.net_config(side_in=64, num_joints=17, **textra)
+    scfg = po.net_config(side_in=64, num_joints=17, **sextra)
+    orc = po.DistillOracle(po.init_state("depthnet", "resnet18", scfg, seed=11), "depthnet", "resnet18", scfg,
+                           po.init_state(tkind, "resnet18", tcfg, seed=21), tkind, tcfg, key_index=16, **dkw)
+    batch = po.synth_distill_batch(2, 64, 17, stride=16, seed=3)
+    cams, dists, gns = [], [], []
+    for it in range(2):
+        cam, dist, gn, spec, last = orc.step(batch, 0.3)
+        cams.append(cam); dists.append(dist); gns.append(gn)
+        if it == 0:
+            assert rel_err(spec, g[f"{tag}_spec"]) < 1e-5
+            assert rel_err(last[:, :8], g[f"{tag}_last_slice"]) < 1e-5
+    np.testing.assert_allclose(cams, g[f"{tag}_cam"], rtol=2e-4)
+    np.testing.assert_allclose(dists, g[f"{tag}_dist"], rtol=2e-4)
+    np.testing.assert_allclose(gns, g[f"{tag}_gn"], rtol=5e-3)
+    np.testing.assert_allclose(orc.tsd["bn1.running_mean"].numpy(), g[f"{tag}_teacher_bn1_rm"], rtol=1e-4, atol=1e-6)
