@@ -196,6 +196,22 @@ int b2_mimic_loss_bwd(const void* teach, const void* student, const float* atten
 int b2_attention_map(const float* image_coords, int32_t N, int32_t J, int32_t side_in, int32_t side_out,
                      float* out, void* stream);
 
+/* ---- on-device input pipeline (the per-sample CPU work of depth_datasets.py:153-217) -----
+ * Homography crop = cameralib.reproject_image_fast (cameralib.py:667-711): cv2.remap semantics (INTER_LINEAR,
+ * coordinates rounded to 1/32 pixel, constant 0 border).  homography: DEVICE float[N][9] (row major,
+ * destination pixel -> source pixel, i.e. old_K old_R inv(new_K new_R) in float32).
+ * rgb  : src uint8 [N,Hs,Ws,3] -> dst fp32 [N,3,S,S] = ((remap / 255) - mean) / std   (ToTensor + Normalize,
+ *        depth_datasets.py:92-94); mean3 / std3 are HOST float[3].
+ * depth: src fp32 [N,Hs,Ws] (homography NULL: already cropped [N,S,S]) -> remap -> optional utils.to_depth with
+ *        the sample's camera (cam: DEVICE float[N][6] = inv(K[:2,:2]) row major | K[0,2], K[1,2]; NULL = skip)
+ *        -> optional enhance_ntu / enhance_pku (depth_datasets.py:39-56: x = v / (10/255); nexponent ?
+ *        exp(-x) * (veil_threshold <= x) : x / 3; threshold 0.1 for NTU, 0.5 for PKU) -> dst fp32 [N,1,S,S]. */
+int b2_remap_normalize_rgb(const uint8_t* src, int32_t N, int32_t Hs, int32_t Ws, const float* homography,
+                           int32_t side_out, const float* mean3, const float* std3, float* dst, void* stream);
+int b2_remap_enhance_depth(const float* src, int32_t N, int32_t Hs, int32_t Ws, const float* homography,
+                           int32_t side_out, const float* cam, float veil_threshold, int32_t nexponent,
+                           int32_t do_enhance, float* dst, void* stream);
+
 /* ---- MaxPool2d(3, stride 2, pad 1) on x and veil together: partial_depthnet.py:219-220 --- */
 int b2_maxpool3x3s2_fwd(const void* x, const float* veil_in, void* y, uint8_t* argmax, float* veil_out,
                         int32_t N, int32_t H, int32_t W, int32_t C, int32_t dtype, void* stream);

@@ -389,6 +389,75 @@ def gen_distill(ref):
     return out
 
 
+# ------------------------------------------------------------------ input pipeline
+def _reference_functions(path, names):
+    """Compile selected top-level functions straight from a reference source file (the module itself does not
+    import here: jpeg4py, matplotlib, pickle5 ... are absent) -- the reference's code runs, nothing is copied."""
+    import ast
+    tree = ast.parse(open(path).read())
+    ns = {"np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def gen_pipeline(ref):
+    import copy
+    import torchvision.transforms as transforms
+    CL, U = ref["cameralib"], ref["utils"]
+    if not hasattr(np, "float"):
+        np.float = float                      # the reference predates numpy 1.24 (depth_datasets.py:42)
+    enhance_ntu, enhance_pku = _reference_functions(os.path.join(REF, "depth_datasets.py"), ["enhance_ntu", "enhance_pku"])
+    transform = transforms.Compose([transforms.ToTensor(),
+                                    transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    rng = np.random.RandomState(7)
+    out, names = {}, []
+    side = 48
+    for name, (Hs, Ws, f, bbox, flip, zoom) in dict(
+            centre=(120, 160, 130.0, (50, 20, 40, 80), False, 1.0),
+            corner_flip=(120, 160, 130.0, (100, 50, 50, 60), True, 0.9),       # crop leaves the frame: border pixels
+            wide=(90, 128, 95.0, (10, 30, 90, 40), False, 1.15)).items():
+        K = np.array([[f, 0, Ws / 2], [0, f * 1.02, Hs / 2], [0, 0, 1]], np.float32)
+        camera = CL.Camera(intrinsic_matrix=K, world_up=(0, -1, 0))
+        bbox = np.array(bbox, np.float64)
+        # get_input_image, depth_datasets.py:153-198, executed on the reference's Camera
+        center = bbox[:2] + bbox[2:] / 2
+        width, height = np.array([bbox[2] / 2, 0]), np.array([0, bbox[3] / 2])
+        far_side = np.stack([center - height, center + height]) if bbox[2] < bbox[3] else np.stack([center - width, center + width])
+        new_cam = copy.deepcopy(camera)
+        new_cam.turn_towards(center)
+        new_cam.undistort()
+        new_cam.square_pixels()
+        far = new_cam.world_to_image(camera.image_to_world(far_side))
+        new_cam.zoom(side / np.linalg.norm(far[0] - far[1]))
+        new_cam.center_principal_point((side, side))
+        new_cam.zoom(zoom)
+        if flip:
+            new_cam.horizontal_flip()
+        yy, xx = np.mgrid[:Hs, :Ws]
+        color = np.clip(np.stack([xx * 255.0 / Ws, yy * 255.0 / Hs, (xx + yy) % 256], -1) + rng.randint(-40, 40, (Hs, Ws, 3)), 0, 255).astype(np.uint8)
+        depth = (rng.rand(Hs, Ws).astype(np.float32) * 0.08 + 0.002) * (rng.rand(Hs, Ws) > 0.2)
+        depth = depth.astype(np.float32)
+        col_crop = CL.reproject_image(color, camera, new_cam, (side, side))
+        dep_crop = CL.reproject_image(depth, camera, new_cam, (side, side))
+        hom = po.homography(camera.intrinsic_matrix, camera.R, new_cam.intrinsic_matrix, new_cam.R)
+        assert np.array_equal(po.remap_bilinear(color, hom, (side, side)), col_crop), name
+        out.update({f"{name}_color": color, f"{name}_depth": depth, f"{name}_hom": hom, f"{name}_K": K,
+                    f"{name}_K_old": camera.intrinsic_matrix, f"{name}_R_old": camera.R,
+                    f"{name}_K_new": new_cam.intrinsic_matrix, f"{name}_R_new": new_cam.R,
+                    f"{name}_color_crop": col_crop, f"{name}_depth_crop": dep_crop[..., 0],
+                    f"{name}_color_out": np_(transform(col_crop.copy()))})
+        d = dep_crop.squeeze()
+        out[f"{name}_ntu_exp"] = enhance_ntu(d, True)
+        out[f"{name}_ntu_lin"] = enhance_ntu(d, False)
+        out[f"{name}_pku_exp"] = enhance_pku(d, True)
+        out[f"{name}_todepth_ntu_exp"] = enhance_ntu(U.to_depth(d, camera), True)      # depth_datasets.py:214-217
+        names.append(name)
+    out["names"] = np.array(names)
+    return out
+
+
 def gen_shapes(ref):
     """KA7: parameter counts and output shapes of the full-size nets (no forward needed for counts)."""
     out = {}
@@ -404,9 +473,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ref = import_reference()
-    which = sys.argv[1:] or ["ka", "pconv", "head", "to_depth", "shapes", "nets", "distill"]
+    which = sys.argv[1:] or ["ka", "pconv", "head", "to_depth", "shapes", "nets", "distill", "pipeline"]
     table = dict(ka=gen_known_answers, pconv=gen_pconv_cases, head=gen_head, to_depth=gen_to_depth,
-                 shapes=gen_shapes, nets=gen_nets, distill=gen_distill)
+                 shapes=gen_shapes, nets=gen_nets, distill=gen_distill, pipeline=gen_pipeline)
     for name in which:
         data = table[name](ref)
         path = os.path.join(OUT, f"{name}.npz")

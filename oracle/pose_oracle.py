@@ -557,6 +557,74 @@ class DistillOracle(StepOracle):
         return float(cam), float(dist), float(gn), spec.detach(), last.detach()
 
 
+# ----------------------------------------------------------------------------
+# input pipeline (depth_datasets.py:39-56,153-217; cameralib.py:667-711)
+# ----------------------------------------------------------------------------
+
+
+def homography(old_K, old_R, new_K, new_R):
+    """cameralib.reproject_image_fast, cameralib.py:672-674.  The matrices keep their own dtypes (a Camera
+    holds float32 members, but square_pixels() / zoom() leave a float64 intrinsic matrix behind), so the
+    products round exactly as the reference's do."""
+    old_matrix = np.asarray(old_K) @ np.asarray(old_R)
+    new_matrix = np.asarray(new_K) @ np.asarray(new_R)
+    return (old_matrix @ np.linalg.inv(new_matrix)).astype(np.float32)
+
+
+def remap_bilinear(image, hom, out_shape):
+    """cv2.remap(image, x, y, INTER_LINEAR, BORDER_CONSTANT 0) with the maps of cameralib.py:690-693,
+    restated from OpenCV's documented behaviour (4.x imgproc/imgwarp.cpp, `remap` + `remapBilinear`):
+    coordinates rounded to 1/32 px (cvRound(v * INTER_TAB_SIZE)), 2-D weights = products of {1-f/32, f/32};
+    uint8: 15-bit fixed-point weights, (sum + 2^14) >> 15; float: fp32 weighted sum; neighbours outside
+    the frame read the border value.  image: [H, W] or [H, W, C]; returns [Ho, Wo(, C)]."""
+    Ho, Wo = out_shape
+    y, x = np.mgrid[:Ho, :Wo].astype(np.float32)
+    coords = np.stack([x, y, np.ones_like(x)], axis=0).reshape(3, -1)
+    coords = np.asarray(hom, np.float32) @ coords
+    coords = coords[:2] / coords[2:]
+    sx = np.rint(np.clip(coords[0] * np.float32(32), -1e9, 1e9)).astype(np.int64)
+    sy = np.rint(np.clip(coords[1] * np.float32(32), -1e9, 1e9)).astype(np.int64)
+    ix, iy, fx, fy = sx >> 5, sy >> 5, sx & 31, sy & 31
+    img = image if image.ndim == 3 else image[..., None]
+    H, W, Cc = img.shape
+
+    def fetch(yy, xx):
+        ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+        v = img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)]
+        return np.where(ok[:, None], v, 0)
+
+    p00, p01, p10, p11 = fetch(iy, ix), fetch(iy, ix + 1), fetch(iy + 1, ix), fetch(iy + 1, ix + 1)
+    if img.dtype == np.uint8:
+        w00, w01 = (32 - fx) * (32 - fy) * 32, fx * (32 - fy) * 32
+        w10, w11 = (32 - fx) * fy * 32, fx * fy * 32
+        acc = (p00.astype(np.int64) * w00[:, None] + p01.astype(np.int64) * w01[:, None]
+               + p10.astype(np.int64) * w10[:, None] + p11.astype(np.int64) * w11[:, None] + (1 << 14)) >> 15
+        out = acc.astype(np.uint8)
+    else:
+        ax, ay = fx.astype(np.float32) / np.float32(32), fy.astype(np.float32) / np.float32(32)
+        w00, w01 = (1 - ay) * (1 - ax), (1 - ay) * ax
+        w10, w11 = ay * (1 - ax), ay * ax
+        out = (p00.astype(np.float32) * w00[:, None] + p01.astype(np.float32) * w01[:, None]
+               + p10.astype(np.float32) * w10[:, None] + p11.astype(np.float32) * w11[:, None]).astype(np.float32)
+    out = out.reshape(Ho, Wo, Cc)
+    return out if image.ndim == 3 else out[..., 0]
+
+
+def enhance(image, nexponent, data_name="ntu"):
+    """enhance_ntu / enhance_pku, depth_datasets.py:39-56 (np.float there is float64)."""
+    image = image / (10.0 / 255.0)
+    veil = ((0.1 if data_name == "ntu" else 0.5) <= image).astype(np.float64)
+    dest = np.multiply(np.exp(-image), veil) if nexponent else (image / 3.0)
+    return dest.astype(np.float32)[np.newaxis, :, :]
+
+
+def normalize_rgb(image_u8, mean=(0.485, 0.456, 0.406), dev=(0.229, 0.224, 0.225)):
+    """transforms.Compose([ToTensor(), Normalize(mean, dev)]), depth_datasets.py:92-94: HWC uint8 -> CHW fp32."""
+    t = torch.from_numpy(np.ascontiguousarray(image_u8)).permute(2, 0, 1).float().div(255)
+    m, s = torch.tensor(mean).view(3, 1, 1), torch.tensor(dev).view(3, 1, 1)
+    return (t - m) / s
+
+
 def learn_rate_at(epoch, *, learn_rate=5e-5, warmup=1, warmup_factor=0.2, learn_decay=0.2):
     """depth_train.py:621-638."""
     e = epoch - 1

@@ -204,3 +204,25 @@ def test_distill_step(golden_dir, tag):
     np.testing.assert_allclose(dists, g[f"{tag}_dist"], rtol=2e-4)
     np.testing.assert_allclose(gns, g[f"{tag}_gn"], rtol=5e-3)
     np.testing.assert_allclose(orc.tsd["bn1.running_mean"].numpy(), g[f"{tag}_teacher_bn1_rm"], rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------ input pipeline
+def test_pipeline(golden_dir):
+    g = load(golden_dir, "pipeline")
+    for name in g["names"]:
+        hom = po.homography(g[f"{name}_K_old"], g[f"{name}_R_old"], g[f"{name}_K_new"], g[f"{name}_R_new"])
+        assert np.array_equal(hom, g[f"{name}_hom"])
+        side = g[f"{name}_color_crop"].shape[0]
+        crop = po.remap_bilinear(g[f"{name}_color"], hom, (side, side))
+        assert np.array_equal(crop, g[f"{name}_color_crop"]), name                   # cv2.remap, bit exact (uint8)
+        np.testing.assert_allclose(po.normalize_rgb(crop).numpy(), g[f"{name}_color_out"], rtol=1e-6, atol=1e-7)
+        dcrop = po.remap_bilinear(g[f"{name}_depth"], hom, (side, side))
+        np.testing.assert_allclose(dcrop, g[f"{name}_depth_crop"], rtol=1e-6, atol=1e-9)
+        d = g[f"{name}_depth_crop"]
+        np.testing.assert_allclose(po.enhance(d, True, "ntu"), g[f"{name}_ntu_exp"], rtol=1e-6)
+        np.testing.assert_allclose(po.enhance(d, False, "ntu"), g[f"{name}_ntu_lin"], rtol=1e-6)
+        np.testing.assert_allclose(po.enhance(d, True, "pku"), g[f"{name}_pku_exp"], rtol=1e-6)
+        np.testing.assert_allclose(po.enhance(po.to_depth(d, g[f"{name}_K"]), True, "ntu"), g[f"{name}_todepth_ntu_exp"],
+                                   rtol=1e-5)
+        assert g[f"{name}_ntu_exp"].shape == (1, side, side) and (g[f"{name}_ntu_exp"] == 0).any()
+    assert (g["corner_flip_color_crop"] == 0).all(-1).any()          # the crop leaves the frame: border pixels
