@@ -11,4 +11,4 @@ from . import _lib, ops, layers, nets, utils, pipeline  # noqa: F401
 from . import partial_conv, depthnet, partial_depthnet, fusionnet, partial_fusionnet, resnet  # noqa: F401
 from .layers import PartialConv, PartialConv2d, Conv2d, BatchNorm2d  # noqa: F401
 from .trainer import Trainer, train_args, synthetic_batch  # noqa: F401
-from .utils import to_heatmap, decode, to_depth, heatmap_coords, pose_loss, mpjpe, mimic_loss, get_attention  # noqa: F401
+from .utils import to_heatmap, decode, to_depth, heatmap_coords, pose_loss, mpjpe, mimic_loss, get_attention, analyze, parse_epoch, MetricAccumulator  # noqa: F401

@@ -404,3 +404,83 @@ extern "C" int b2_pose_loss(const float* coords, const float* true_cam, const ui
   B2_LAUNCH_CHECK("pose_loss");
   return B2_OK;
 }
+
+// ---------------------------------------------------------------- evaluation metrics
+// utils.analyze + utils.statistics (utils.py:197-262) and the back-rotation einsum of the test loops
+// (depth_train.py:522-523) for one batch, accumulated into acc[10] (double):
+//   [0] valid joints  [1] sum dist  [2] #(dist <= rough)  [3] sum max(0, 1 - dist / rough)
+//   [4] solid [5] close [6] depth [7] jitter [8] switch [9] fail      (the sequential elimination of :210-221)
+// Epoch totals of these give parse_epoch's batch-size-weighted means exactly (utils.py:224-231).
+namespace {
+__global__ void pose_metrics_kernel(const float* __restrict__ spec, const float* __restrict__ truth,
+                                    const uint8_t* __restrict__ valid, const float* __restrict__ rot,
+                                    const int* __restrict__ mirror, int N, int J, float t_solid, float t_close,
+                                    float t_rough, double* __restrict__ acc) {
+  __shared__ double red[10][8];
+  double v[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) v[k] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * J; i += gridDim.x * blockDim.x) {
+    if (!valid[i]) continue;
+    const int n = i / J, j = i - n * J;
+    const int jm = mirror ? mirror[j] : j;
+    const float* s = spec + (long long)i * 3;
+    const float* t = truth + (long long)i * 3;
+    const float* tm = truth + ((long long)n * J + jm) * 3;
+    float ds[3] = {s[0] - t[0], s[1] - t[1], s[2] - t[2]};
+    float df[3] = {s[0] - tm[0], s[1] - tm[1], s[2] - tm[2]};
+    if (rot) {                                   // R (s - t): distances are rotation invariant, the tangent part is not
+      const float* r = rot + (long long)n * 9;
+      float a[3], b[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        a[q] = r[q * 3] * ds[0] + r[q * 3 + 1] * ds[1] + r[q * 3 + 2] * ds[2];
+        b[q] = r[q * 3] * df[0] + r[q * 3 + 1] * df[1] + r[q * 3 + 2] * df[2];
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { ds[q] = a[q]; df[q] = b[q]; }
+    }
+    const float basic = sqrtf(ds[0] * ds[0] + ds[1] * ds[1] + ds[2] * ds[2]);
+    const float flip = sqrtf(df[0] * df[0] + df[1] * df[1] + df[2] * df[2]);
+    const float tangent = sqrtf(ds[0] * ds[0] + ds[1] * ds[1]);
+    v[0] += 1.0;
+    v[1] += (double)basic;
+    v[2] += (basic / t_rough <= 1.0f) ? 1.0 : 0.0;
+    v[3] += (double)fmaxf(0.f, 1.f - basic / t_rough);
+    int cat;
+    if (basic <= t_solid) cat = 4;
+    else if (basic <= t_close) cat = 5;
+    else if (tangent <= t_close) cat = 6;
+    else if (basic <= t_rough) cat = 7;
+    else if (flip <= t_rough) cat = 8;
+    else cat = 9;
+#pragma unroll
+    for (int k = 4; k < 10; ++k) v[k] += (cat == k) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    double x = v[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    double x = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += red[threadIdx.x][w];
+    atomicAdd(acc + threadIdx.x, x);
+  }
+}
+}  // namespace
+
+extern "C" int b2_pose_metrics(const float* spec_cam, const float* true_cam, const uint8_t* valid,
+                               const float* back_rotate, const int32_t* mirror, int32_t N, int32_t J, float t_solid,
+                               float t_close, float t_rough, double* acc, void* stream) {
+  B2_REQUIRE(spec_cam && true_cam && valid && acc && N > 0 && J > 0, B2_E_BADARG, "pose_metrics: bad argument");
+  B2_REQUIRE(t_rough > 0.f, B2_E_BADARG, "pose_metrics: the rough threshold must be positive");
+  int blocks = (N * J + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  pose_metrics_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(spec_cam, true_cam, valid, back_rotate, mirror, N, J,
+                                                             t_solid, t_close, t_rough, acc);
+  B2_LAUNCH_CHECK("pose_metrics");
+  return B2_OK;
+}

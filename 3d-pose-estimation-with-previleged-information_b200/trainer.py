@@ -141,6 +141,9 @@ class Trainer:
         self.grad_norm, self.loss_div = g("grad_norm", 5.0), g("loss_div", 10.0)
         self.weight_decay = g("weight_decay", 4e-5)
         self.criterion = g("criterion", "SmoothL1")
+        self.thresh = g("thresh", None)                 # dict(solid=, close=, rough=) mm: depth_train.py:62 / train.py:47-51
+        if self.thresh is None and g("thresh_rough", None) is not None:
+            self.thresh = dict(solid=g("thresh_solid", None), close=g("thresh_close", None), rough=g("thresh_rough", None))
         if self.criterion not in ops.CRITERIA:
             raise ValueError("criterion must be one of %s" % sorted(ops.CRITERIA))
         self.legacy = getattr(model, "kind", "") == "resnet"           # train.py:174 has no loss_div
@@ -513,6 +516,54 @@ class Trainer:
         if self.do_fusion:
             return self.fusion_train(epoch, data_loader, self.device)
         return self.vanilla_train(epoch, data_loader, self.device)
+
+    # ------------------------------------------------------------------ evaluation loops (depth_train.py:477-618)
+    @torch.no_grad()
+    def _test_epoch(self, epoch, test_loader, device=None):
+        """fusion_test / vanilla_test: eval forward + head + loss per batch, back-rotation and the
+        analyze / parse_epoch metrics accumulated on the device (one read-back per epoch).
+        test_loader yields (color, depth, true_cam, true_val, back_rotate)."""
+        thresh = getattr(self, "thresh", None)
+        if thresh is None:
+            raise RuntimeError("set trainer.thresh = dict(solid=, close=, rough=) (metadata['thresholds'], "
+                               "depth_train.py:62) before testing")
+        mirror = self.data_info.get("mirror") if isinstance(self.data_info, dict) else getattr(self.data_info, "mirror", None)
+        acc = utils.MetricAccumulator(mirror, thresh, self.device)
+        n_batches = len(test_loader)
+        loss_avg, total = 0.0, 0
+        for i_batch, (color, depth, true_cam, true_val, back_rotate) in enumerate(test_loader):
+            color, depth = color.to(self.device), depth.to(self.device)
+            true_cam, true_val = true_cam.to(self.device), true_val.to(self.device)
+            loss, spec = self._forward_loss(color, depth, true_cam,
+                                            true_val.view(torch.uint8) if true_val.dtype == torch.bool else true_val)
+            acc.update(spec, true_cam, true_val, torch.as_tensor(back_rotate).to(self.device))
+            n = true_cam.size(0)
+            val = loss.item()
+            loss_avg += val * n
+            total += n
+            print("| test Epoch[%d] [%d/%d]  Cam Loss %1.4f" % (epoch, i_batch, n_batches, val), flush=True)
+        loss_avg /= max(total, 1)
+        record = dict(test_loss=loss_avg)
+        res = acc.result()
+        res.pop("batch_size")
+        record.update(res)
+        print("\n=> test Epoch[%d]  Cam Loss: %1.4f\n" % (epoch, loss_avg))
+        print("=>[SPEC] cam_mean: %1.3f  [pck]: %1.3f  [auc]: %1.3f\n"
+              % (record["cam_mean"], record["score_pck"], record["score_auc"]))
+        return record
+
+    def fusion_test(self, epoch, test_loader, device=None):
+        return self._test_epoch(epoch, test_loader, device)
+
+    def vanilla_test(self, epoch, test_loader, device=None):
+        return self._test_epoch(epoch, test_loader, device)
+
+    cam_test = vanilla_test
+
+    def test(self, epoch, test_loader):
+        """depth_train.py:610-618."""
+        self.model.eval()
+        return self._test_epoch(epoch, test_loader, self.device)
 
     @torch.no_grad()
     def predict(self, batch):

@@ -70,6 +70,54 @@ def to_depth(image, depth_cam):
     return out.cpu().numpy()
 
 
+METRIC_KEYS = ("solid", "close", "depth", "jitter", "switch", "fail")
+
+
+class MetricAccumulator:
+    """Epoch-level ``utils.analyze`` + ``utils.parse_epoch`` (utils.py:197-262) on the device: every batch
+    is one kernel launch into a 10-double accumulator; ``result()`` is the single host read-back.  The
+    batch-size-weighted means of parse_epoch equal the ratios of the epoch totals kept here."""
+
+    def __init__(self, mirror, thresh, device):
+        self.thresh = (float(thresh["solid"]), float(thresh["close"]), float(thresh["rough"]))
+        self.mirror = None if mirror is None else torch.as_tensor(np.asarray(mirror, np.int32)).to(device)
+        self.acc = torch.zeros(10, dtype=torch.float64, device=device)
+
+    def update(self, spec_cam, true_cam, valid_mask, back_rotate=None):
+        L = ops.L
+        L.require_cuda(spec_cam, true_cam, valid_mask, back_rotate)
+        spec = spec_cam.detach().float().contiguous()
+        true = true_cam.detach().float().contiguous()
+        valid = valid_mask.to(torch.uint8).contiguous()
+        rot = None if back_rotate is None else back_rotate.detach().float().contiguous()
+        N, J, _ = spec.shape
+        L.call("b2_pose_metrics", L.ptr(spec), L.ptr(true), L.ptr(valid), L.ptr(rot), L.ptr(self.mirror), N, J,
+               self.thresh[0], self.thresh[1], self.thresh[2], L.ptr(self.acc), L.stream())
+
+    def result(self):
+        a = self.acc.cpu().numpy()
+        n = max(a[0], 1.0)
+        out = {k: float(a[4 + i] / n) for i, k in enumerate(METRIC_KEYS)}
+        out.update(score_pck=float(a[2] / n), score_auc=float(a[3] / n), cam_mean=float(a[1] / n), batch_size=int(a[0]))
+        return out
+
+
+def analyze(spec_cam, true_cam, valid_mask, mirror, thresh, back_rotate=None):
+    """utils.analyze (utils.py:234-262) for CUDA tensors: dict(batch_size, score_pck, score_auc, cam_mean and the
+    error taxonomy solid / close / depth / jitter / switch / fail).  ``back_rotate`` [N,3,3] applies the
+    einsum of the test loops (depth_train.py:522-523) first."""
+    acc = MetricAccumulator(mirror, thresh, spec_cam.device)
+    acc.update(spec_cam, true_cam, valid_mask, back_rotate)
+    return acc.result()
+
+
+def parse_epoch(stats):
+    """utils.parse_epoch (utils.py:224-231): batch-size weighted means of a list of ``analyze`` dicts."""
+    keys = ("solid", "close", "jitter", "depth", "switch", "fail", "score_pck", "score_auc", "cam_mean", "batch_size")
+    values = np.array([[patch[key] for patch in stats] for key in keys], np.float64)
+    return dict(zip(keys[:-1], np.sum(values[-1] * values[:-1], axis=1) / np.sum(values[-1])))
+
+
 def mpjpe(spec_cam, true_cam, valid):
     """``cam_mean`` of utils.analyze (utils.py:253-262): mean joint distance (mm) over valid joints."""
     d = torch.linalg.norm(spec_cam.float() - true_cam.float(), dim=-1).reshape(-1)

@@ -196,6 +196,15 @@ int b2_mimic_loss_bwd(const void* teach, const void* student, const float* atten
 int b2_attention_map(const float* image_coords, int32_t N, int32_t J, int32_t side_in, int32_t side_out,
                      float* out, void* stream);
 
+/* ---- evaluation metrics: utils.analyze / statistics (utils.py:197-262) with the back-rotation of the
+ * test loops (depth_train.py:522-523), accumulated over batches.  spec_cam / true_cam: [N,J,3] fp32 mm,
+ * valid: [N,J] uint8, back_rotate: [N,3,3] fp32 or NULL, mirror: int32[J] or NULL (identity).
+ * acc (double[10], ADDED to): valid joints, sum dist, #(dist <= rough), sum max(0, 1 - dist/rough),
+ * then the error taxonomy counts solid / close / depth / jitter / switch / fail (utils.py:210-221). */
+int b2_pose_metrics(const float* spec_cam, const float* true_cam, const uint8_t* valid, const float* back_rotate,
+                    const int32_t* mirror, int32_t N, int32_t J, float t_solid, float t_close, float t_rough,
+                    double* acc, void* stream);
+
 /* ---- on-device input pipeline (the per-sample CPU work of depth_datasets.py:153-217) -----
  * Homography crop = cameralib.reproject_image_fast (cameralib.py:667-711): cv2.remap semantics (INTER_LINEAR,
  * coordinates rounded to 1/32 pixel, constant 0 border).  homography: DEVICE float[N][9] (row major,

@@ -389,6 +389,41 @@ def gen_distill(ref):
     return out
 
 
+# ------------------------------------------------------------------ evaluation metrics
+def gen_metrics(ref):
+    U = ref["utils"]
+    rng = np.random.RandomState(3)
+    out = {}
+    thresh = dict(solid=50.0, close=100.0, rough=150.0)
+    mirror = np.array([0, 2, 1, 4, 3, 5, 7, 6, 8, 10, 9, 12, 11, 14, 13, 16, 15])
+    batches = []
+    for b, N in enumerate((5, 8, 3)):
+        true = (rng.randn(N, 17, 3) * 300).astype(np.float32)
+        spec = true + (rng.randn(N, 17, 3) * rng.choice([10.0, 60.0, 200.0], (N, 17, 1))).astype(np.float32)
+        swap = rng.rand(N, 17) < 0.1                       # some left/right switches
+        spec[swap] = true[:, mirror][swap] + (rng.randn(int(swap.sum()), 3) * 20).astype(np.float32)
+        deep = rng.rand(N, 17) < 0.1                       # some pure depth errors
+        spec[deep, 2] += 400.0
+        valid = rng.rand(N, 17) < 0.85
+        q, _ = np.linalg.qr(rng.randn(N, 3, 3))
+        rot = q.astype(np.float32)
+        # depth_train.py:522-527 executed with the reference's utils.analyze
+        s = np.einsum("Bij,BCj->BCi", rot, spec)
+        t = np.einsum("Bij,BCj->BCi", rot, true)
+        stats = U.analyze(s, t, valid, mirror, thresh)
+        batches.append(stats)
+        out.update({f"b{b}_spec": spec, f"b{b}_true": true, f"b{b}_valid": valid, f"b{b}_rot": rot})
+        for k, v in stats.items():
+            out[f"b{b}_{k}"] = np.array(v, np.float64)
+    epoch = U.parse_epoch(batches)
+    for k, v in epoch.items():
+        out[f"epoch_{k}"] = np.array(v, np.float64)
+    out["mirror"] = mirror
+    out["thresh"] = np.array([thresh["solid"], thresh["close"], thresh["rough"]], np.float64)
+    out["n_batches"] = np.array(3)
+    return out
+
+
 # ------------------------------------------------------------------ input pipeline
 def _reference_functions(path, names):
     """Compile selected top-level functions straight from a reference source file (the module itself does not
@@ -473,9 +508,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ref = import_reference()
-    which = sys.argv[1:] or ["ka", "pconv", "head", "to_depth", "shapes", "nets", "distill", "pipeline"]
+    which = sys.argv[1:] or ["ka", "pconv", "head", "to_depth", "shapes", "nets", "distill", "pipeline", "metrics"]
     table = dict(ka=gen_known_answers, pconv=gen_pconv_cases, head=gen_head, to_depth=gen_to_depth,
-                 shapes=gen_shapes, nets=gen_nets, distill=gen_distill, pipeline=gen_pipeline)
+                 shapes=gen_shapes, nets=gen_nets, distill=gen_distill, pipeline=gen_pipeline, metrics=gen_metrics)
     for name in which:
         data = table[name](ref)
         path = os.path.join(OUT, f"{name}.npz")

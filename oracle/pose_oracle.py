@@ -558,6 +558,52 @@ class DistillOracle(StepOracle):
 
 
 # ----------------------------------------------------------------------------
+# evaluation metrics (utils.py:197-262, depth_train.py:522-527)
+# ----------------------------------------------------------------------------
+
+
+def statistics(basic, flip, tangent, thresh):
+    """utils.statistics, utils.py:197-221: sequential elimination into the error taxonomy."""
+    dist = dict(basic=basic, flip=flip, tangent=tangent)
+
+    def count_and_eliminate(condition):
+        remains = np.nonzero(np.logical_not(condition))
+        for k in dist:
+            dist[k] = dist[k][remains]
+        return np.count_nonzero(condition)
+
+    count = float(dist["basic"].size)
+    solid = count_and_eliminate(dist["basic"] <= thresh["solid"]) / count
+    close = count_and_eliminate(dist["basic"] <= thresh["close"]) / count
+    depth = count_and_eliminate(dist["tangent"] <= thresh["close"]) / count
+    jitter = count_and_eliminate(dist["basic"] <= thresh["rough"]) / count
+    switch = count_and_eliminate(dist["flip"] <= thresh["rough"]) / count
+    return dict(solid=solid, close=close, depth=depth, jitter=jitter, switch=switch, fail=dist["basic"].size / count)
+
+
+def analyze(spec_cam, true_cam, valid_mask, mirror, thresh, back_rotate=None):
+    """utils.analyze, utils.py:234-262, after the back-rotation einsum of depth_train.py:522-523."""
+    if back_rotate is not None:
+        spec_cam = np.einsum("Bij,BCj->BCi", back_rotate, spec_cam)
+        true_cam = np.einsum("Bij,BCj->BCi", back_rotate, true_cam)
+    valid = valid_mask.flatten()
+    dist = np.linalg.norm(spec_cam - true_cam, axis=-1).flatten()[valid]
+    dist_flip = np.linalg.norm(spec_cam - true_cam[:, mirror], axis=-1).flatten()[valid]
+    dist_tangent = np.linalg.norm(spec_cam[:, :, :2] - true_cam[:, :, :2], axis=-1).flatten()[valid]
+    stats = statistics(dist, dist_flip, dist_tangent, thresh)
+    stats.update(batch_size=dist.shape[0], score_pck=np.mean(dist / thresh["rough"] <= 1.0),
+                 score_auc=np.mean(np.maximum(0, 1 - dist / thresh["rough"])), cam_mean=np.mean(dist))
+    return stats
+
+
+def parse_epoch(stats):
+    """utils.parse_epoch, utils.py:224-231."""
+    keys = ("solid", "close", "jitter", "depth", "switch", "fail", "score_pck", "score_auc", "cam_mean", "batch_size")
+    values = np.array([[patch[key] for patch in stats] for key in keys])
+    return dict(zip(keys[:-1], np.sum(values[-1] * values[:-1], axis=1) / np.sum(values[-1])))
+
+
+# ----------------------------------------------------------------------------
 # input pipeline (depth_datasets.py:39-56,153-217; cameralib.py:667-711)
 # ----------------------------------------------------------------------------
 

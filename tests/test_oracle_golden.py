@@ -226,3 +226,20 @@ def test_pipeline(golden_dir):
                                    rtol=1e-5)
         assert g[f"{name}_ntu_exp"].shape == (1, side, side) and (g[f"{name}_ntu_exp"] == 0).any()
     assert (g["corner_flip_color_crop"] == 0).all(-1).any()          # the crop leaves the frame: border pixels
+
+
+# ------------------------------------------------------------------ evaluation metrics
+def test_metrics(golden_dir):
+    g = load(golden_dir, "metrics")
+    thresh = dict(zip(("solid", "close", "rough"), g["thresh"]))
+    keys = ("solid", "close", "depth", "jitter", "switch", "fail", "score_pck", "score_auc", "cam_mean", "batch_size")
+    stats = []
+    for b in range(int(g["n_batches"])):
+        s = po.analyze(g[f"b{b}_spec"], g[f"b{b}_true"], g[f"b{b}_valid"], g["mirror"], thresh, g[f"b{b}_rot"])
+        for k in keys:
+            np.testing.assert_allclose(s[k], g[f"b{b}_{k}"], rtol=1e-6), (b, k)
+        assert abs(sum(s[k] for k in keys[:6]) - 1.0) < 1e-12            # the taxonomy partitions the valid joints
+        stats.append(s)
+    ep = po.parse_epoch(stats)
+    for k in keys[:-1]:
+        np.testing.assert_allclose(ep[k], g[f"epoch_{k}"], rtol=1e-6)
