@@ -1306,8 +1306,14 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   p.bricks_per_split = (int)((bricks + want - 1) / want);
   p.splits = (int)((bricks + p.bricks_per_split - 1) / p.bricks_per_split);
   const int stage_bytes = 2 * kWgPix * 128 + p.T * (p.BNc / 64) * kWgPix * 128;
-  int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars)) / stage_bytes;
+  // B2POSE_WGRAD_SMEM_KB caps the ring so that blocks of other kernels (the BatchNorm streams running on the
+  // main stream while wgrad runs on the side stream) can share the SM
+  static const int env_kb = getenv("B2POSE_WGRAD_SMEM_KB") ? atoi(getenv("B2POSE_WGRAD_SMEM_KB")) : 0;
+  int budget = smem_limit();
+  if (env_kb > 0 && env_kb * 1024 < budget) budget = env_kb * 1024;
+  int stages = (budget - 2048 - (int)sizeof(PipeBars)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.T * p.BNc);
   p.dw = dw_out;

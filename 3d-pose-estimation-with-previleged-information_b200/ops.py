@@ -93,7 +93,7 @@ def bn_totals(C_, device):
     return torch.zeros(2 * C_, dtype=torch.float32, device=device)
 
 
-def workspace(nbytes, device):
+def workspace(nbytes, device, slot=0):
     """Grow-only scratch buffer per device, shared by all calls (the kernels that use it run on one
     stream, in order).  It is deliberately NOT keyed by stream: under CUDA-graph capture the current
     stream is the capture stream, and a buffer first allocated there would live in that graph's private
@@ -102,13 +102,13 @@ def workspace(nbytes, device):
     any capture."""
     if nbytes == 0:
         return None, 0
-    ws = _workspaces.get(device.index)
+    ws = _workspaces.get((device.index, slot))
     if ws is None or ws.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("libb2pose workspace would have to grow during CUDA-graph capture; run the "
                                "same shapes eagerly once before capturing")
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[device.index] = ws
+        _workspaces[(device.index, slot)] = ws
     return ws, ws.numel()
 
 
@@ -202,7 +202,54 @@ def _conv_dgrad(desc, dy, ratio, wk, mask, addend=None):
     return dx if addend is None else dx + addend
 
 
+# ---- weight gradients on a side stream ------------------------------------------------------------
+# dW of a layer is needed only by the optimizer, so inside a managed training step (`wgrad_overlap_begin`
+# ... `wgrad_overlap_end`, used by the Trainer) the wgrad kernels are enqueued on a second stream and run
+# concurrently with the BatchNorm-backward / dgrad chain of the following layers: they fill the tails of
+# the persistent kernels and overlap the HBM-bound BatchNorm streams.  Every tensor a side-stream kernel
+# reads is kept alive until the streams join (the caching allocator would otherwise hand its memory to
+# the main stream while the side stream still reads it); the side stream has its own scratch workspace.
+class _Overlap:
+    __slots__ = ("stream", "keep", "active", "main")
+
+    def __init__(self):
+        self.stream, self.keep, self.active, self.main = None, [], False, None
+
+
+_overlaps = {}
+_WGRAD_OVERLAP = __import__("os").environ.get("B2POSE_WGRAD_OVERLAP", "1") != "0"
+
+
+def wgrad_overlap_begin(device):
+    if not _WGRAD_OVERLAP:
+        return
+    o = _overlaps.setdefault(device.index, _Overlap())
+    if o.stream is None:
+        o.stream = torch.cuda.Stream(device=device)
+    o.keep, o.active, o.main = [], True, torch.cuda.current_stream(device)
+
+
+def wgrad_overlap_end(device):
+    """Join: the main stream waits for every side-stream wgrad; the kept tensors are released."""
+    o = _overlaps.get(device.index)
+    if o is None or not o.active:
+        return
+    o.main.wait_stream(o.stream)
+    o.keep, o.active, o.main = [], False, None
+
+
 def _conv_wgrad(desc, x, mask, dy, ratio, sink=None):
+    o = _overlaps.get(dy.device.index)
+    if o is None or not o.active or sink is None:
+        return _conv_wgrad_now(desc, x, mask, dy, ratio, sink, 0)
+    o.stream.wait_stream(torch.cuda.current_stream(dy.device))      # dy (and x) are ready
+    o.keep.append((x, mask, dy, ratio))
+    with torch.cuda.stream(o.stream):
+        _conv_wgrad_now(desc, x, mask, dy, ratio, sink, 1)
+    return None
+
+
+def _conv_wgrad_now(desc, x, mask, dy, ratio, sink=None, ws_slot=0):
     """dw (fp32, KRSC) accumulated into ``sink`` (a [K,C,R,S] channels_last view of the flat gradient
     buffer; returns None) or into a fresh zero tensor (returned as logical [K,C,R,S])."""
     dev = dy.device
@@ -212,7 +259,7 @@ def _conv_wgrad(desc, x, mask, dy, ratio, sink=None):
             raise RuntimeError("gradient sink must be an fp32 channels_last view")
     else:
         dw = torch.zeros((desc.K, desc.R, desc.S, desc.C), dtype=torch.float32, device=dev)
-    ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 2), dev)
+    ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 2), dev, ws_slot)
     L.call("b2_pconv_wgrad", C.byref(desc), L.ptr(x), L.ptr(mask), L.ptr(dy), L.ptr(ratio), L.ptr(dw),
            L.ptr(ws), wsn, L.stream())
     return None if sink is not None else dw.permute(0, 3, 1, 2)
@@ -357,13 +404,13 @@ class ConvBNFn(Function):
         # dy now holds dRaw = dOut * ratio -> tell the conv kernels not to scale again
         desc.flags |= L.CONV_DY_PRESCALED
         dx = dw = None
-        if ctx.needs_input_grad[0]:
-            addend = ctx.dx_holder.pop("dres", None) if ctx.dx_holder is not None else None
-            dx = _conv_dgrad(desc, dy, None, wk, mask, addend)
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[2]:        # first: on the side stream it then runs beside this layer's dgrad
             dw = _conv_wgrad(desc, x, mask, dy, None, sinks[0] if sinks is not None else None)
             if dw is not None:
                 dw = dw.to(ctx.wdtype)
+        if ctx.needs_input_grad[0]:
+            addend = ctx.dx_holder.pop("dres", None) if ctx.dx_holder is not None else None
+            dx = _conv_dgrad(desc, dy, None, wk, mask, addend)
         desc.flags &= ~L.CONV_DY_PRESCALED
         if sinks is not None:
             dgamma = dbeta = None

@@ -287,6 +287,7 @@ class Trainer:
     def _fwd_bwd(self, batch, semi=None):
         self.flat.g.zero_()
         ops.bn_arena_begin(self.device)          # zeroed per-channel accumulators of the totals BatchNorm path
+        ops.wgrad_overlap_begin(self.device)     # weight gradients run on a side stream until the join below
         try:
             if semi is not None:
                 loss, spec = self._forward_loss(*batch, semi=semi)
@@ -294,6 +295,7 @@ class Trainer:
                 loss, spec = self._forward_loss(*batch)
             loss.backward()
         finally:
+            ops.wgrad_overlap_end(self.device)
             ops.bn_arena_end(self.device)
         return loss.detach(), spec
 
