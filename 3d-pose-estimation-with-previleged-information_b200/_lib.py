@@ -50,9 +50,9 @@ SIGNATURES = {
     "b2_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _l, _i, _i, _p],
     "b2_bn_totals_supported": [_i, _i],
     "b2_bn_stats_totals": [_p, _l, _i, _i, _p, _p],
-    "b2_bn_apply_totals": [_p, _p, _l, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _p],
-    "b2_bn_bwd_reduce_totals": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _l, _i, _i, _p],
-    "b2_bn_bwd_apply_totals": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p],
+    "b2_bn_apply_totals": [_p, _p, _l, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _p],
+    "b2_bn_bwd_reduce_totals": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _l, _i, _i, _p],
+    "b2_bn_bwd_apply_totals": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _i, _i, _p],
     "b2_mimic_loss_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p],
     "b2_mimic_loss_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "b2_attention_map": [_p, _i, _i, _i, _i, _p, _p],

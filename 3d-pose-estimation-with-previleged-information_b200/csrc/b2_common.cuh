@@ -196,14 +196,14 @@ int bn_stream_stats(const void* y, int64_t rows, int C, float* partials, int tot
 int bn_stream_apply_fin(const void* y, const void* residual, void* z, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, const float* row_mask, int relu, int64_t rows, int C,
                         int mode, const float* totals, float* running_mean, float* running_var, float momentum,
-                        float eps, float* mean_out, float* invstd_out, cudaStream_t st);
+                        float eps, float* mean_out, float* invstd_out, uint8_t* gate_out, cudaStream_t st);
 int bn_stream_apply(const void* y, const void* residual, void* z, const float* mean, const float* invstd,
                     const float* gamma, const float* beta, const float* row_mask, int relu, int64_t rows, int C,
                     cudaStream_t st);
 int bn_stream_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const float* row_mask, int relu, float* partials,
-                         int totals, int64_t rows, int C, cudaStream_t st);
+                         int totals, const uint8_t* gate, int64_t rows, int C, cudaStream_t st);
 int bn_stream_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, const float* gsum, const float* row_mask,
                         const float* row_scale, int relu, int training, void* dy, void* d_residual, float* dgamma,
-                        float* dbeta, int64_t rows, int C, cudaStream_t st);
+                        float* dbeta, const uint8_t* gate, int64_t rows, int C, cudaStream_t st);

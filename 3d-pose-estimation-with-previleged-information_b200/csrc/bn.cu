@@ -433,7 +433,7 @@ extern "C" int b2_bn_bwd_reduce(const void* dz, const void* z, const void* y, co
   B2_REQUIRE((C & 3) == 0, B2_E_UNSUPPORTED, "bn_bwd_reduce: C=%d is not a multiple of 4", C);
   cudaStream_t st = (cudaStream_t)stream;
   if (bn_stream_eligible(C, dtype))
-    return bn_stream_bwd_reduce(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, partials, 0, rows, C, st);
+    return bn_stream_bwd_reduce(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, partials, 0, nullptr, rows, C, st);
   const int nv = vec_width(C, dtype);
   Geo g = geometry(rows, C / nv, 16, 2, true);
   size_t sh = 2 * sizeof(float) * nv * g.block.x * g.block.y;
@@ -469,7 +469,7 @@ extern "C" int b2_bn_bwd_apply(const void* dz, const void* z, const void* y, con
   cudaStream_t st = (cudaStream_t)stream;
   if (bn_stream_eligible(C, dtype))
     return bn_stream_bwd_apply(dz, z, y, mean, invstd, gamma, beta, gsum, row_mask, row_scale, relu, training, dy,
-                               d_residual, nullptr, nullptr, rows, C, st);
+                               d_residual, nullptr, nullptr, nullptr, rows, C, st);
   const int nv = vec_width(C, dtype);
   Geo g = geometry(rows, C / nv, 8, 4);
   if (dtype == B2_F32)
@@ -501,35 +501,37 @@ extern "C" int b2_bn_apply_totals(const void* y, const float* totals, int64_t ro
                                   float* running_var, float momentum, float eps, int32_t training,
                                   const float* gamma, const float* beta, const void* residual,
                                   const float* row_mask, int32_t relu, void* z, float* mean, float* invstd,
-                                  int32_t C, int32_t dtype, void* stream) {
+                                  uint8_t* gate_out, int32_t C, int32_t dtype, void* stream) {
   B2_REQUIRE(y && z && gamma && beta && mean && invstd && rows > 0 && C > 0, B2_E_BADARG, "bn_apply_totals: bad argument");
   B2_REQUIRE(training ? (totals != nullptr) : (running_mean && running_var), B2_E_BADARG,
              "bn_apply_totals: statistics source missing");
   B2_REQUIRE(bn_stream_eligible(C, dtype), B2_E_UNSUPPORTED, "bn_apply_totals: C=%d dtype=%d has no totals path", C, dtype);
   return bn_stream_apply_fin(y, residual, z, nullptr, nullptr, gamma, beta, row_mask, relu, rows, C, training ? 1 : 2,
-                             totals, running_mean, running_var, momentum, eps, mean, invstd, (cudaStream_t)stream);
+                             totals, running_mean, running_var, momentum, eps, mean, invstd, gate_out,
+                             (cudaStream_t)stream);
 }
 
 extern "C" int b2_bn_bwd_reduce_totals(const void* dz, const void* z, const void* y, const float* mean,
                                        const float* invstd, const float* gamma, const float* beta,
-                                       const float* row_mask, int32_t relu, float* gsum, int64_t rows, int32_t C,
-                                       int32_t dtype, void* stream) {
-  B2_REQUIRE(dz && y && mean && invstd && gsum && rows > 0 && C > 0 && (!relu || z || (gamma && beta)), B2_E_BADARG,
+                                       const float* row_mask, int32_t relu, float* gsum, const uint8_t* gate,
+                                       int64_t rows, int32_t C, int32_t dtype, void* stream) {
+  B2_REQUIRE(dz && y && mean && invstd && gsum && rows > 0 && C > 0 && (!relu || z || gate || (gamma && beta)), B2_E_BADARG,
              "bn_bwd_reduce_totals: bad argument");
   B2_REQUIRE(bn_stream_eligible(C, dtype), B2_E_UNSUPPORTED, "bn_bwd_reduce_totals: C=%d dtype=%d has no totals path", C,
              dtype);
-  return bn_stream_bwd_reduce(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, gsum, 1, rows, C, (cudaStream_t)stream);
+  return bn_stream_bwd_reduce(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, gsum, 1, gate, rows, C,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int b2_bn_bwd_apply_totals(const void* dz, const void* z, const void* y, const float* mean,
                                       const float* invstd, const float* gamma, const float* beta, const float* gsum,
                                       const float* row_mask, const float* row_scale, int32_t relu, int32_t training,
-                                      void* dy, void* d_residual, float* dgamma, float* dbeta, int64_t rows,
-                                      int32_t C, int32_t dtype, void* stream) {
-  B2_REQUIRE(dz && y && mean && invstd && gamma && gsum && dy && rows > 0 && C > 0 && (!relu || z || beta), B2_E_BADARG,
+                                      void* dy, void* d_residual, float* dgamma, float* dbeta, const uint8_t* gate,
+                                      int64_t rows, int32_t C, int32_t dtype, void* stream) {
+  B2_REQUIRE(dz && y && mean && invstd && gamma && gsum && dy && rows > 0 && C > 0 && (!relu || z || gate || beta), B2_E_BADARG,
              "bn_bwd_apply_totals: bad argument");
   B2_REQUIRE(bn_stream_eligible(C, dtype), B2_E_UNSUPPORTED, "bn_bwd_apply_totals: C=%d dtype=%d has no totals path", C,
              dtype);
   return bn_stream_bwd_apply(dz, z, y, mean, invstd, gamma, beta, gsum, row_mask, row_scale, relu, training, dy,
-                             d_residual, dgamma, dbeta, rows, C, (cudaStream_t)stream);
+                             d_residual, dgamma, dbeta, gate, rows, C, (cudaStream_t)stream);
 }

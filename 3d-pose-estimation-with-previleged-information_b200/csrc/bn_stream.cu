@@ -56,15 +56,19 @@ struct Ring {
   uint64_t* full;    // [kStagesS]
   const uint8_t* src[NIN];
   long long total_bytes;
+  const uint8_t* bits = nullptr;   // optional 1-bit-per-element side stream (ReLU gate): kChunkBytes / 16 bytes per chunk
+  uint8_t* bits_buf = nullptr;     // [kStagesS][kChunkBytes / 16]
 
   __device__ __forceinline__ void issue(int stage, long long chunk) {
     const long long off = chunk * kChunkBytes;
     long long rem = total_bytes - off;
     const uint32_t bytes = (uint32_t)(rem < kChunkBytes ? rem : kChunkBytes);
-    s_mbar_expect(&full[stage], bytes * NIN);
+    const uint32_t gb = bits ? ((bytes >> 4) + 15u) & ~15u : 0u;       // bulk copies move multiples of 16 bytes
+    s_mbar_expect(&full[stage], bytes * NIN + gb);
 #pragma unroll
     for (int i = 0; i < NIN; ++i)
       s_bulk_load(buf + ((size_t)stage * NIN + i) * kChunkBytes, src[i] + off, bytes, &full[stage]);
+    if (bits) s_bulk_load(bits_buf + (size_t)stage * (kChunkBytes / 16), bits + (off >> 4), gb, &full[stage]);
   }
   __device__ __forceinline__ const bf16* data(int stage, int i) const {
     return reinterpret_cast<const bf16*>(buf + ((size_t)stage * NIN + i) * kChunkBytes);
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(kThreadsS, 3)
 apply_stream_kernel(const bf16* __restrict__ y, const bf16* __restrict__ residual, bf16* __restrict__ z,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ row_mask, int relu,
-                    long long total_elems, int C, const ApplyFin fin) {
+                    long long total_elems, int C, const ApplyFin fin, uint8_t* __restrict__ gate_out) {
   pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   const int CV = C >> 3, cv = threadIdx.x % CV, logC = 31 - __clz(C);
@@ -227,14 +231,17 @@ apply_stream_kernel(const bf16* __restrict__ y, const bf16* __restrict__ residua
           load8(ring.data(stage, 0) + v * 8, f);
           if (has_res) load8(ring.data(stage, 1) + v * 8, g);
           const float mk = row_mask ? row_mask[e >> logC] : 1.f;
+          uint32_t bits = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float a = fmaf(f[j], sc[j], sh[j]);
             if (has_res) a += g[j];
+            bits |= (a > 0.f ? 1u : 0u) << j;
             if (relu) a = fmaxf(a, 0.f);
             f[j] = a * mk;
           }
           store8(z + e, f);
+          if (gate_out) gate_out[e >> 3] = (uint8_t)bits;      // ReLU gate of residual layers: 1 bit per element
         }
       }
       __syncthreads();
@@ -260,6 +267,7 @@ apply_stream_kernel(const bf16* __restrict__ y, const bf16* __restrict__ residua
 // ---------------------------------------------------------------- backward: shared pieces
 struct BwdArgs {
   const bf16 *dz, *z, *y;
+  const uint8_t* gate;         // GSRC 2: ReLU gate bitmask written by the forward apply (1 bit per element)
   const float *mean, *invstd, *gamma, *beta, *row_mask, *row_scale, *gsum;
   int relu, training;
   bf16 *dy, *d_residual;
@@ -271,8 +279,11 @@ struct BwdArgs {
 };
 
 // MODE 0: reduce (partials of g and g*xhat);  MODE 1: apply (dy, d_residual)
-template <int MODE, bool HASZ>
+// GSRC: where the ReLU gate comes from -- 0: recomputed from y (or no ReLU), 1: the saved output z (third
+// input stream), 2: the forward's gate bitmask (one byte per 16-byte vector, read straight from global memory)
+template <int MODE, int GSRC>
 __global__ void __launch_bounds__(kThreadsS, 3) bwd_stream_kernel(const BwdArgs a) {
+  constexpr bool HASZ = GSRC == 1;
   pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NIN = HASZ ? 3 : 2;
@@ -280,10 +291,14 @@ __global__ void __launch_bounds__(kThreadsS, 3) bwd_stream_kernel(const BwdArgs 
   ring.src[0] = reinterpret_cast<const uint8_t*>(a.dz);
   ring.src[1] = reinterpret_cast<const uint8_t*>(a.y);
   if (HASZ) ring.src[NIN - 1] = reinterpret_cast<const uint8_t*>(a.z);
+  if (GSRC == 2) {       // the gate bytes ride the same ring (behind the barriers and the reduction scratch)
+    ring.bits = a.gate;
+    ring.bits_buf = smem + (size_t)kStagesS * NIN * kChunkBytes + 64 + (MODE == 0 ? 2 * kThreadsS * 8 * sizeof(float) : 0);
+  }
   ring_setup(ring, smem, a.total_elems * 2);
   float* red = reinterpret_cast<float*>(smem + (size_t)kStagesS * NIN * kChunkBytes + 64);
   const int C = a.C, CV = C >> 3, cv = threadIdx.x % CV, logC = 31 - __clz(C);
-  const bool regate = a.relu && !HASZ;
+  const bool regate = a.relu && GSRC == 0;
   // forward scale/shift (gate recompute), and either (mu) for the reduce or (A, B, D) for the apply
   float sc[8], sh[8], k0[8], k1[8], k2[8];
 #pragma unroll
@@ -333,6 +348,10 @@ __global__ void __launch_bounds__(kThreadsS, 3) bwd_stream_kernel(const BwdArgs 
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = zz[j] > 0.f ? g[j] : 0.f;
           }
+        } else if (GSRC == 2) {
+          const uint32_t bits = ring.bits_buf[(size_t)stage * (kChunkBytes / 16) + v];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = ((bits >> j) & 1u) ? g[j] : 0.f;
         } else if (regate) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) g[j] = fmaf(f[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
@@ -376,8 +395,9 @@ inline bool enabled() {
   return v == 1;
 }
 
-inline size_t smem_bytes(int nin, bool reduce) {
-  return (size_t)kStagesS * nin * kChunkBytes + 64 + (reduce ? 2 * kThreadsS * 8 * sizeof(float) : 0);
+inline size_t smem_bytes(int nin, bool reduce, bool bits = false) {
+  return (size_t)kStagesS * nin * kChunkBytes + 64 + (reduce ? 2 * kThreadsS * 8 * sizeof(float) : 0) +
+         (bits ? (size_t)kStagesS * (kChunkBytes / 16) : 0);
 }
 
 inline int stream_grid(long long total_elems, int blocks_per_sm, bool slots) {
@@ -417,13 +437,13 @@ int bn_stream_apply(const void* y, const void* residual, void* z, const float* m
                     const float* gamma, const float* beta, const float* row_mask, int relu, int64_t rows, int C,
                     cudaStream_t st) {
   return bn_stream_apply_fin(y, residual, z, mean, invstd, gamma, beta, row_mask, relu, rows, C, 0, nullptr, nullptr,
-                             nullptr, 0.f, 0.f, nullptr, nullptr, st);
+                             nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, st);
 }
 
 int bn_stream_apply_fin(const void* y, const void* residual, void* z, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, const float* row_mask, int relu, int64_t rows, int C,
                         int mode, const float* totals, float* running_mean, float* running_var, float momentum,
-                        float eps, float* mean_out, float* invstd_out, cudaStream_t st) {
+                        float eps, float* mean_out, float* invstd_out, uint8_t* gate_out, cudaStream_t st) {
   ApplyFin fin{};
   fin.mode = mode; fin.totals = totals; fin.rows = rows; fin.running_mean = running_mean;
   fin.running_var = running_var; fin.momentum = momentum; fin.eps = eps; fin.mean_out = mean_out;
@@ -432,7 +452,8 @@ int bn_stream_apply_fin(const void* y, const void* residual, void* z, const floa
   int rc = opt_in(apply_stream_kernel, sh);
   if (rc) return rc;
   launch_pdl(apply_stream_kernel, dim3(stream_grid(rows * C, 3, false)), dim3(kThreadsS), sh, st, (const bf16*)y,
-             (const bf16*)residual, (bf16*)z, mean, invstd, gamma, beta, row_mask, relu, (long long)(rows * C), C, fin);
+             (const bf16*)residual, (bf16*)z, mean, invstd, gamma, beta, row_mask, relu, (long long)(rows * C), C, fin,
+             gate_out);
   B2_LAUNCH_CHECK("bn_apply(stream)");
   return B2_OK;
 }
@@ -448,19 +469,22 @@ static BwdArgs make_bwd(const void* dz, const void* z, const void* y, const floa
 
 int bn_stream_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const float* row_mask, int relu, float* partials,
-                         int totals, int64_t rows, int C, cudaStream_t st) {
+                         int totals, const uint8_t* gate, int64_t rows, int C, cudaStream_t st) {
   BwdArgs a = make_bwd(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, rows, C);
-  a.partials = partials; a.totals = totals;
-  const bool hasz = relu && z != nullptr;
-  const size_t sh = smem_bytes(hasz ? 3 : 2, true);
+  a.partials = partials; a.totals = totals; a.gate = gate;
+  const int gsrc = !relu ? 0 : (gate ? 2 : (z ? 1 : 0));
+  const size_t sh = smem_bytes(gsrc == 1 ? 3 : 2, true, gsrc == 2);
   const int grid = stream_grid(rows * C, 2, true);
   int rc;
-  if (hasz) {
-    if ((rc = opt_in(bwd_stream_kernel<0, true>, sh))) return rc;
-    launch_pdl(bwd_stream_kernel<0, true>, dim3(grid), dim3(kThreadsS), sh, st, a);
+  if (gsrc == 1) {
+    if ((rc = opt_in(bwd_stream_kernel<0, 1>, sh))) return rc;
+    launch_pdl(bwd_stream_kernel<0, 1>, dim3(grid), dim3(kThreadsS), sh, st, a);
+  } else if (gsrc == 2) {
+    if ((rc = opt_in(bwd_stream_kernel<0, 2>, sh))) return rc;
+    launch_pdl(bwd_stream_kernel<0, 2>, dim3(grid), dim3(kThreadsS), sh, st, a);
   } else {
-    if ((rc = opt_in(bwd_stream_kernel<0, false>, sh))) return rc;
-    launch_pdl(bwd_stream_kernel<0, false>, dim3(grid), dim3(kThreadsS), sh, st, a);
+    if ((rc = opt_in(bwd_stream_kernel<0, 0>, sh))) return rc;
+    launch_pdl(bwd_stream_kernel<0, 0>, dim3(grid), dim3(kThreadsS), sh, st, a);
   }
   B2_LAUNCH_CHECK("bn_bwd_reduce(stream)");
   return B2_OK;
@@ -469,20 +493,23 @@ int bn_stream_bwd_reduce(const void* dz, const void* z, const void* y, const flo
 int bn_stream_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, const float* gsum, const float* row_mask,
                         const float* row_scale, int relu, int training, void* dy, void* d_residual, float* dgamma,
-                        float* dbeta, int64_t rows, int C, cudaStream_t st) {
+                        float* dbeta, const uint8_t* gate, int64_t rows, int C, cudaStream_t st) {
   BwdArgs a = make_bwd(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, rows, C);
-  a.dgamma = dgamma; a.dbeta = dbeta;
+  a.dgamma = dgamma; a.dbeta = dbeta; a.gate = gate;
   a.gsum = gsum; a.row_scale = row_scale; a.training = training; a.dy = (bf16*)dy; a.d_residual = (bf16*)d_residual;
-  const bool hasz = relu && z != nullptr;
-  const size_t sh = smem_bytes(hasz ? 3 : 2, false);
+  const int gsrc = !relu ? 0 : (gate ? 2 : (z ? 1 : 0));
+  const size_t sh = smem_bytes(gsrc == 1 ? 3 : 2, false, gsrc == 2);
   const int grid = stream_grid(rows * C, 3, false);
   int rc;
-  if (hasz) {
-    if ((rc = opt_in(bwd_stream_kernel<1, true>, sh))) return rc;
-    launch_pdl(bwd_stream_kernel<1, true>, dim3(grid), dim3(kThreadsS), sh, st, a);
+  if (gsrc == 1) {
+    if ((rc = opt_in(bwd_stream_kernel<1, 1>, sh))) return rc;
+    launch_pdl(bwd_stream_kernel<1, 1>, dim3(grid), dim3(kThreadsS), sh, st, a);
+  } else if (gsrc == 2) {
+    if ((rc = opt_in(bwd_stream_kernel<1, 2>, sh))) return rc;
+    launch_pdl(bwd_stream_kernel<1, 2>, dim3(grid), dim3(kThreadsS), sh, st, a);
   } else {
-    if ((rc = opt_in(bwd_stream_kernel<1, false>, sh))) return rc;
-    launch_pdl(bwd_stream_kernel<1, false>, dim3(grid), dim3(kThreadsS), sh, st, a);
+    if ((rc = opt_in(bwd_stream_kernel<1, 0>, sh))) return rc;
+    launch_pdl(bwd_stream_kernel<1, 0>, dim3(grid), dim3(kThreadsS), sh, st, a);
   }
   B2_LAUNCH_CHECK("bn_bwd_apply(stream)");
   return B2_OK;

@@ -349,10 +349,15 @@ class ConvBNFn(Function):
         if residual is not None:
             residual = residual.contiguous()
         row_mask = mask_out if (mask_output and partial) else None
+        gate = None
         if fast:
+            if relu and residual is not None:
+                # ReLU gate of a residual layer as a bitmask (1/16 of z's bytes) for the two backward passes
+                gate = torch.empty((rows * K // 8 + 15) // 16 * 16, dtype=torch.uint8, device=x.device)
             L.call("b2_bn_apply_totals", L.ptr(y), L.ptr(sums), rows, L.ptr(running_mean), L.ptr(running_var),
                    float(momentum), float(eps), int(training), L.ptr(gamma), L.ptr(beta), L.ptr(residual),
-                   L.ptr(row_mask), int(relu), L.ptr(z), L.ptr(mean), L.ptr(invstd), K, L.dt(y), L.stream())
+                   L.ptr(row_mask), int(relu), L.ptr(z), L.ptr(mean), L.ptr(invstd), L.ptr(gate), K, L.dt(y),
+                   L.stream())
         else:
             L.call("b2_bn_finalize", L.ptr(sums), rows, K, L.ptr(running_mean), L.ptr(running_var), float(momentum),
                    float(eps), int(training), L.ptr(mean), L.ptr(invstd), L.stream())
@@ -364,15 +369,16 @@ class ConvBNFn(Function):
         ctx.sinks = sinks
         ctx.dx_holder, ctx.res_holder = dx_holder, res_holder
         # z is only needed for the ReLU gate of residual layers; otherwise the gate is recomputed from y
-        ctx.save_for_backward(x, mask if partial else None, wk, ratio, y, z if (relu and residual is not None) else None,
-                              mean, invstd, gamma.detach(), beta.detach(), row_mask)
+        ctx.save_for_backward(x, mask if partial else None, wk, ratio, y,
+                              z if (relu and residual is not None and gate is None) else None,
+                              mean, invstd, gamma.detach(), beta.detach(), row_mask, gate)
         if partial:
             ctx.mark_non_differentiable(mask_out)
         return z, mask_out
 
     @staticmethod
     def backward(ctx, dz, _dmask):
-        x, mask, wk, ratio, y, z, mean, invstd, gamma, beta, row_mask = ctx.saved_tensors
+        x, mask, wk, ratio, y, z, mean, invstd, gamma, beta, row_mask, gate = ctx.saved_tensors
         desc = ctx.desc
         dz = dz.contiguous()
         dev = dz.device
@@ -388,10 +394,10 @@ class ConvBNFn(Function):
         if ctx.fast:
             gsum = bn_totals(K, dev)
             L.call("b2_bn_bwd_reduce_totals", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
-                   L.ptr(beta), L.ptr(row_mask), int(ctx.relu), L.ptr(gsum), rows, K, L.dt(dz), L.stream())
+                   L.ptr(beta), L.ptr(row_mask), int(ctx.relu), L.ptr(gsum), L.ptr(gate), rows, K, L.dt(dz), L.stream())
             L.call("b2_bn_bwd_apply_totals", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
                    L.ptr(beta), L.ptr(gsum), L.ptr(row_mask), L.ptr(ratio), int(ctx.relu), int(ctx.training),
-                   L.ptr(dy), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), rows, K, L.dt(dz), L.stream())
+                   L.ptr(dy), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), L.ptr(gate), rows, K, L.dt(dz), L.stream())
         else:
             parts = bn_partials(K, dev)
             L.call("b2_bn_bwd_reduce", L.ptr(dz), L.ptr(z), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma),

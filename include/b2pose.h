@@ -161,20 +161,23 @@ int b2_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* m
 int b2_bn_totals_supported(int32_t C, int32_t dtype);
 int b2_bn_stats_totals(const void* y, int64_t rows, int32_t C, int32_t dtype, float* totals, void* stream);
 /* training != 0: batch statistics from `totals`, running stats updated (momentum, unbiased var);
- * training == 0: running stats (totals may be NULL).  Writes z and mean[C], invstd[C]. */
+ * training == 0: running stats (totals may be NULL).  Writes z and mean[C], invstd[C].
+ * gate_out (optional, uint8[rows*C/8 rounded up to a multiple of 16 bytes]): bit j of byte v = (pre-ReLU value of element 8v+j > 0) -- the ReLU
+ * gate of a residual layer, 1/16 of the bytes of z; pass it as `gate` to the two backward calls (z = NULL). */
 int b2_bn_apply_totals(const void* y, const float* totals, int64_t rows, float* running_mean,
                        float* running_var, float momentum, float eps, int32_t training, const float* gamma,
                        const float* beta, const void* residual, const float* row_mask, int32_t relu, void* z,
-                       float* mean, float* invstd, int32_t C, int32_t dtype, void* stream);
+                       float* mean, float* invstd, uint8_t* gate_out, int32_t C, int32_t dtype, void* stream);
 int b2_bn_bwd_reduce_totals(const void* dz, const void* z, const void* y, const float* mean,
                             const float* invstd, const float* gamma, const float* beta, const float* row_mask,
-                            int32_t relu, float* gsum, int64_t rows, int32_t C, int32_t dtype, void* stream);
+                            int32_t relu, float* gsum, const uint8_t* gate, int64_t rows, int32_t C, int32_t dtype,
+                            void* stream);
 /* as b2_bn_bwd_apply; additionally dgamma += gsum[C:2C], dbeta += gsum[0:C] (either may be NULL) */
 int b2_bn_bwd_apply_totals(const void* dz, const void* z, const void* y, const float* mean,
                            const float* invstd, const float* gamma, const float* beta, const float* gsum,
                            const float* row_mask, const float* row_scale, int32_t relu, int32_t training,
-                           void* dy, void* d_residual, float* dgamma, float* dbeta, int64_t rows, int32_t C,
-                           int32_t dtype, void* stream);
+                           void* dy, void* d_residual, float* dgamma, float* dbeta, const uint8_t* gate, int64_t rows,
+                           int32_t C, int32_t dtype, void* stream);
 
 /* ---- feature-mimic (distillation) loss -------------------------------------------------
  * replaces Trainer.distill, depth_train.py:115-129 (the "privileged information" term):

@@ -188,13 +188,15 @@ def test_bn_totals_path_matches_slot_path(b2pose, dev, C, rows, relu, res):
                    P(ratio), relu, 1, P(dy), P(dres), rows, C, L.BF16, st)
         else:
             totals, gsum = torch.zeros(2 * C, device=dev), torch.zeros(2 * C, device=dev)
+            # residual + ReLU layers hand the gate over as a bitmask instead of the saved output z
+            gate = torch.empty((rows * C // 8 + 15) // 16 * 16, dtype=torch.uint8, device=dev) if (relu and res) else None
             L.call("b2_bn_stats_totals", P(y), rows, C, L.BF16, P(totals), st)
             L.call("b2_bn_apply_totals", P(y), P(totals), rows, P(rm), P(rv), 0.1, 1e-5, 1, P(gamma), P(beta), P(resid),
-                   P(row_mask), relu, P(z), P(mean), P(invstd), C, L.BF16, st)
-            L.call("b2_bn_bwd_reduce_totals", P(dz), P(zsave), P(y), P(mean), P(invstd), P(gamma), P(beta), P(row_mask),
-                   relu, P(gsum), rows, C, L.BF16, st)
-            L.call("b2_bn_bwd_apply_totals", P(dz), P(zsave), P(y), P(mean), P(invstd), P(gamma), P(beta), P(gsum),
-                   P(row_mask), P(ratio), relu, 1, P(dy), P(dres), P(dgamma), P(dbeta), rows, C, L.BF16, st)
+                   P(row_mask), relu, P(z), P(mean), P(invstd), P(gate), C, L.BF16, st)
+            L.call("b2_bn_bwd_reduce_totals", P(dz), None, P(y), P(mean), P(invstd), P(gamma), P(beta), P(row_mask),
+                   relu, P(gsum), P(gate), rows, C, L.BF16, st)
+            L.call("b2_bn_bwd_apply_totals", P(dz), None, P(y), P(mean), P(invstd), P(gamma), P(beta), P(gsum),
+                   P(row_mask), P(ratio), relu, 1, P(dy), P(dres), P(dgamma), P(dbeta), P(gate), rows, C, L.BF16, st)
         torch.cuda.synchronize()
         out[mode] = dict(mean=mean, invstd=invstd, rm=rm, rv=rv, z=z.float(), dy=dy.float(), gsum=gsum, dgamma=dgamma,
                          dbeta=dbeta, dres=None if dres is None else dres.float())
@@ -209,7 +211,7 @@ def test_bn_totals_path_matches_slot_path(b2pose, dev, C, rows, relu, res):
     mean2, invstd2, z2 = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty_like(y)
     rm, rv = a["rm"].clone(), a["rv"].clone()
     L.call("b2_bn_apply_totals", P(y), None, rows, P(rm), P(rv), 0.1, 1e-5, 0, P(gamma), P(beta), P(resid), P(row_mask),
-           relu, P(z2), P(mean2), P(invstd2), C, L.BF16, st)
+           relu, P(z2), P(mean2), P(invstd2), None, C, L.BF16, st)
     mean3, invstd3, z3 = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty_like(y)
     L.call("b2_bn_finalize", None, rows, C, P(rm), P(rv), 0.1, 1e-5, 0, P(mean3), P(invstd3), st)
     L.call("b2_bn_apply", P(y), P(mean3), P(invstd3), P(gamma), P(beta), P(resid), P(row_mask), relu, P(z3), rows, C,
