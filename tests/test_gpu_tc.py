@@ -36,6 +36,9 @@ CASES = [
     ("stem_rgb_odd",  2, 3,    64,  65, 65, 7, 2, 3, 1, False, False, False),
     ("stem_c4",       1, 4,    64,  32, 32, 7, 2, 3, 1, False, False, False),
     ("smallc_5x5",    2, 3,    32,  20, 20, 5, 1, 2, 1, False, False, False),
+    # halo-tile mode (3x3 stride 1, Ho % 16 == 0, Wo % 8 == 0): several tiles per image, two channel blocks
+    ("halo_48x40",    3, 128,  64,  48, 40, 3, 1, 1, 1, False, False, False),
+    ("halo_pc_d2",    2, 64,   128, 32, 24, 3, 1, 2, 2, True,  True,  False),
 ]
 
 
