@@ -230,12 +230,26 @@ class ResNet(nn.Module):
         if self.fused:
             if y is None:
                 raise TypeError("forward() of a fusion net takes (color, depth)")
-            a, _ = self._stem(x, self.conv1, self.bn1)
-            b, veil = self._stem(y, self.conv2, self.bn2)
-            a, _ = self._run(self.layer1, a, None)
-            b, veil = self._run(self.layer5, b, veil)
-            a, _ = self._run(self.layer2, a, None)
-            b, veil = self._run(self.layer6, b, veil)
+            if ops.TWO_STREAMS and y.is_cuda:
+                # depth trunk on a second stream, concurrent with the RGB trunk (see ops.branch_stream)
+                main, side = torch.cuda.current_stream(y.device), ops.branch_stream(y.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    b, veil = self._stem(y, self.conv2, self.bn2)
+                    b, veil = self._run(self.layer5, b, veil)
+                    b, veil = self._run(self.layer6, b, veil)
+                a, _ = self._stem(x, self.conv1, self.bn1)
+                a, _ = self._run(self.layer1, a, None)
+                a, _ = self._run(self.layer2, a, None)
+                main.wait_stream(side)
+                b.record_stream(main)            # allocated on the side stream, consumed on this one
+            else:
+                a, _ = self._stem(x, self.conv1, self.bn1)
+                b, veil = self._stem(y, self.conv2, self.bn2)
+                a, _ = self._run(self.layer1, a, None)
+                b, veil = self._run(self.layer5, b, veil)
+                a, _ = self._run(self.layer2, a, None)
+                b, veil = self._run(self.layer6, b, veil)
             f = self.fusion.forward_nhwc(a, b)
         else:
             f, veil = self._stem(x, self.conv1, self.bn1)

@@ -93,6 +93,28 @@ def bn_totals(C_, device):
     return torch.zeros(2 * C_, dtype=torch.float32, device=device)
 
 
+# ---- second stream for the depth branch of the two-stream (fusion) nets ---------------------------
+# RGB trunk (conv1, layer1, layer2) and depth trunk (conv2, layer5, layer6) are independent up to the fusion
+# convolution; the depth trunk is enqueued on its own stream so its kernels fill the launch gaps and tails of
+# the other trunk's persistent kernels (autograd replays each node's backward on the stream of its forward,
+# so the backward pass overlaps the same way).  B2POSE_TWO_STREAMS=0 disables it.
+_branch_streams = {}
+TWO_STREAMS = __import__("os").environ.get("B2POSE_TWO_STREAMS", "1") != "0"
+
+
+def branch_stream(device):
+    st = _branch_streams.get(device.index)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _branch_streams[device.index] = st
+    return st
+
+
+def _on_branch_stream(device):
+    st = _branch_streams.get(device.index)
+    return st is not None and torch.cuda.current_stream(device) == st
+
+
 def workspace(nbytes, device, slot=0):
     """Grow-only scratch buffer per device, shared by all calls (the kernels that use it run on one
     stream, in order).  It is deliberately NOT keyed by stream: under CUDA-graph capture the current
@@ -102,6 +124,8 @@ def workspace(nbytes, device, slot=0):
     any capture."""
     if nbytes == 0:
         return None, 0
+    if slot == 0 and _on_branch_stream(device):
+        slot = 2                     # the concurrent depth branch of the fusion nets has its own scratch
     ws = _workspaces.get((device.index, slot))
     if ws is None or ws.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
