@@ -7,7 +7,7 @@ Public surface = the reference's module surface for this path (SURVEY.md section
 ``libb2pose.so`` (C ABI in ``include/b2pose.h``).  Nothing here falls back to CPU or eager
 PyTorch math: a missing library or a non-CUDA tensor raises.
 """
-from . import _lib, ops, layers, nets, utils, pipeline  # noqa: F401
+from . import _lib, ops, layers, nets, utils, pipeline, mat_utils, back_project  # noqa: F401
 from . import partial_conv, depthnet, partial_depthnet, fusionnet, partial_fusionnet, resnet  # noqa: F401
 from .layers import PartialConv, PartialConv2d, Conv2d, BatchNorm2d  # noqa: F401
 from .trainer import Trainer, train_args, synthetic_batch  # noqa: F401

@@ -59,6 +59,7 @@ SIGNATURES = {
     "b2_pose_metrics": [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p, _p],
     "b2_remap_normalize_rgb": [_p, _i, _i, _i, _p, _i, C.POINTER(_f), C.POINTER(_f), _p, _p],
     "b2_remap_enhance_depth": [_p, _i, _i, _i, _p, _i, _p, _f, _i, _i, _p, _p],
+    "b2_project_points": [_p, _i, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), _p, _p],
     "b2_maxpool3x3s2_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2_maxpool3x3s2_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2_head_fwd": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],

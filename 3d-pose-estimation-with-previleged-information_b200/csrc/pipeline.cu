@@ -112,7 +112,42 @@ remap_depth_kernel(const float* __restrict__ src, int Hs, int Ws, const float* _
   dst[(long long)n * So * So + p] = do_enhance ? enhance(val, thresh, nexponent) : val;
 }
 
+// back_project.projectPoints (back_project.py:12-36): x = K * distort((R X + t) / z), Kd = [k1, k2, p1, p2, k3]
+struct ProjP {
+  float R[9], t[3], K[9], Kd[5];
+};
+__global__ void project_points_kernel(const float* __restrict__ X, int n, ProjP c, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float X0 = X[i], X1 = X[n + i], X2 = X[2 * n + i];                   // X is 3 x N like the reference
+  float x = c.R[0] * X0 + c.R[1] * X1 + c.R[2] * X2 + c.t[0];
+  float y = c.R[3] * X0 + c.R[4] * X1 + c.R[5] * X2 + c.t[1];
+  const float z = c.R[6] * X0 + c.R[7] * X1 + c.R[8] * X2 + c.t[2];
+  x = x / z;
+  y = y / z;
+  const float r = x * x + y * y;
+  const float radial = 1.f + c.Kd[0] * r + c.Kd[1] * r * r + c.Kd[4] * r * r * r;
+  const float xd = x * radial + 2.f * c.Kd[2] * x * y + c.Kd[3] * (r + 2.f * x * x);
+  // the reference overwrites row 0 before computing row 1 (back_project.py:29-30): the cross term uses the DISTORTED x
+  const float yd = y * radial + 2.f * c.Kd[3] * xd * y + c.Kd[2] * (r + 2.f * y * y);
+  out[i] = c.K[0] * xd + c.K[1] * yd + c.K[2];
+  out[n + i] = c.K[3] * xd + c.K[4] * yd + c.K[5];
+  out[2 * n + i] = z;
+}
+
 }  // namespace
+
+extern "C" int b2_project_points(const float* X, int32_t n, const float* R9, const float* t3, const float* K9,
+                                 const float* Kd5, float* out, void* stream) {
+  B2_REQUIRE(X && R9 && t3 && K9 && Kd5 && out && n > 0, B2_E_BADARG, "project_points: bad argument");
+  ProjP c;
+  for (int i = 0; i < 9; ++i) { c.R[i] = R9[i]; c.K[i] = K9[i]; }
+  for (int i = 0; i < 3; ++i) c.t[i] = t3[i];
+  for (int i = 0; i < 5; ++i) c.Kd[i] = Kd5[i];
+  project_points_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(X, n, c, out);
+  B2_LAUNCH_CHECK("project_points");
+  return B2_OK;
+}
 
 extern "C" int b2_remap_normalize_rgb(const uint8_t* src, int32_t N, int32_t Hs, int32_t Ws, const float* homography,
                                       int32_t side_out, const float* mean3, const float* std3, float* dst,

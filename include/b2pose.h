@@ -224,6 +224,12 @@ int b2_remap_enhance_depth(const float* src, int32_t N, int32_t Hs, int32_t Ws, 
                            int32_t side_out, const float* cam, float veil_threshold, int32_t nexponent,
                            int32_t do_enhance, float* dst, void* stream);
 
+/* back_project.projectPoints, back_project.py:12-36: pinhole projection with OpenCV radial / tangential distortion.
+ * X: DEVICE float[3][n] world points; R9, t3, K9, Kd5 = [k1, k2, p1, p2, k3]: HOST arrays (row major);
+ * out: DEVICE float[3][n] = (u, v, camera z). */
+int b2_project_points(const float* X, int32_t n, const float* R9, const float* t3, const float* K9,
+                      const float* Kd5, float* out, void* stream);
+
 /* ---- MaxPool2d(3, stride 2, pad 1) on x and veil together: partial_depthnet.py:219-220 --- */
 int b2_maxpool3x3s2_fwd(const void* x, const float* veil_in, void* y, uint8_t* argmax, float* veil_out,
                         int32_t N, int32_t H, int32_t W, int32_t C, int32_t dtype, void* stream);

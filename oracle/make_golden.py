@@ -389,6 +389,31 @@ def gen_distill(ref):
     return out
 
 
+# ------------------------------------------------------------------ 2-D head + projection
+def gen_head2d(ref):
+    import mat_utils                                   # imports cleanly (torch, numpy, cv2)
+    (projectPoints,) = _reference_functions(os.path.join(REF, "back_project.py"), ["projectPoints"])
+    g = torch.Generator().manual_seed(9)
+    out = {}
+    for name, (N, J, H, W) in (("sq", (2, 19, 17, 17)), ("rect", (3, 5, 9, 13))):
+        feat = (torch.randn(N, J, H, W, generator=g) * 3).requires_grad_(True)
+        heat = mat_utils.to_heatmap(feat, J, H, W)
+        coords = mat_utils.decode(heat, 257.0)
+        cot = torch.randn(N, J, 2, generator=g)
+        (coords * cot).sum().backward()
+        out.update({f"{name}_feat": np_(feat), f"{name}_heat": np_(heat), f"{name}_coords": np_(coords),
+                    f"{name}_cot": np_(cot), f"{name}_dfeat": np_(feat.grad)})
+    rng = np.random.RandomState(2)
+    q, _ = np.linalg.qr(rng.randn(3, 3))
+    cam = dict(K=np.matrix([[1400.0, 0.5, 950.0], [0, 1395.0, 540.0], [0, 0, 1]]), R=np.matrix(q),
+               t=np.matrix(rng.randn(3, 1) * 10 + np.array([[0], [0], [300.0]])),
+               distCoef=np.array([-0.28, 0.11, 1e-3, -5e-4, -0.02]))
+    X = np.matrix(rng.randn(3, 40) * 60.0)
+    out.update(proj_X=np.asarray(X), proj_K=np.asarray(cam["K"]), proj_R=np.asarray(cam["R"]), proj_t=np.asarray(cam["t"]),
+               proj_Kd=cam["distCoef"], proj_out=np.asarray(projectPoints(X, cam)))
+    return out
+
+
 # ------------------------------------------------------------------ evaluation metrics
 def gen_metrics(ref):
     U = ref["utils"]
@@ -429,11 +454,18 @@ def _reference_functions(path, names):
     """Compile selected top-level functions straight from a reference source file (the module itself does not
     import here: jpeg4py, matplotlib, pickle5 ... are absent) -- the reference's code runs, nothing is copied."""
     import ast
-    tree = ast.parse(open(path).read())
+    import re
+    text = open(path).read()
     ns = {"np": np}
-    for node in tree.body:
-        if isinstance(node, ast.FunctionDef) and node.name in names:
-            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    try:
+        tree = ast.parse(text)
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                exec(compile(ast.Module([node], []), path, "exec"), ns)
+    except SyntaxError:                 # a Python-2 file (back_project.py): run just the text of the wanted functions
+        for n in names:
+            m = re.search(r"^def %s\(.*?(?=^\S)" % n, text, flags=re.S | re.M)
+            exec(compile(m.group(0), path, "exec"), ns)
     return [ns[n] for n in names]
 
 
@@ -508,9 +540,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ref = import_reference()
-    which = sys.argv[1:] or ["ka", "pconv", "head", "to_depth", "shapes", "nets", "distill", "pipeline", "metrics"]
+    which = sys.argv[1:] or ["ka", "pconv", "head", "to_depth", "shapes", "nets", "distill", "pipeline", "metrics", "head2d"]
     table = dict(ka=gen_known_answers, pconv=gen_pconv_cases, head=gen_head, to_depth=gen_to_depth,
-                 shapes=gen_shapes, nets=gen_nets, distill=gen_distill, pipeline=gen_pipeline, metrics=gen_metrics)
+                 shapes=gen_shapes, nets=gen_nets, distill=gen_distill, pipeline=gen_pipeline, metrics=gen_metrics, head2d=gen_head2d)
     for name in which:
         data = table[name](ref)
         path = os.path.join(OUT, f"{name}.npz")

@@ -558,6 +558,43 @@ class DistillOracle(StepOracle):
 
 
 # ----------------------------------------------------------------------------
+# 2-D heat-map head (mat_utils.py:31-55) and camera projection (back_project.py:12-36)
+# ----------------------------------------------------------------------------
+
+
+def mat_to_heatmap(ausgabe, num_joints, height, width):
+    """mat_utils.to_heatmap, mat_utils.py:31-41."""
+    heatmap = ausgabe.view(-1, num_joints, height * width)
+    heatmap = torch.exp(heatmap - torch.max(heatmap, dim=2, keepdim=True)[0])
+    heatmap = heatmap / torch.sum(heatmap, dim=2, keepdim=True)
+    return heatmap.view(-1, num_joints, height, width)
+
+
+def mat_decode(heatmap, map_range):
+    """mat_utils.decode, mat_utils.py:44-55."""
+    heat_x, heat_y = torch.sum(heatmap, dim=2), torch.sum(heatmap, dim=3)
+    grid_x = torch.linspace(0.0, 1.0, heat_x.size(-1)).view(1, 1, -1)
+    grid_y = torch.linspace(0.0, 1.0, heat_y.size(-1)).view(1, 1, -1)
+    return torch.stack((torch.sum(grid_x * heat_x, dim=-1), torch.sum(grid_y * heat_y, dim=-1)), dim=2) * map_range
+
+
+def project_points(X, cam):
+    """back_project.projectPoints, back_project.py:12-36 (X: 3 x N)."""
+    K, R, t, Kd = (np.asarray(cam[k], np.float64) for k in ("K", "R", "t", "distCoef"))
+    x = R @ np.asarray(X, np.float64) + t.reshape(3, 1)
+    x[0:2, :] = x[0:2, :] / x[2, :]
+    r = x[0, :] * x[0, :] + x[1, :] * x[1, :]
+    rad = 1 + Kd[0] * r + Kd[1] * r * r + Kd[4] * r * r * r
+    x0 = x[0, :] * rad + 2 * Kd[2] * x[0, :] * x[1, :] + Kd[3] * (r + 2 * x[0, :] * x[0, :])
+    # as written in the reference (:29-30) row 0 is overwritten before row 1 is computed, so the tangential
+    # cross term of row 1 sees the already DISTORTED x -- reproduced, not corrected
+    x1 = x[1, :] * rad + 2 * Kd[3] * x0 * x[1, :] + Kd[2] * (r + 2 * x[1, :] * x[1, :])
+    x[0, :] = K[0, 0] * x0 + K[0, 1] * x1 + K[0, 2]
+    x[1, :] = K[1, 0] * x0 + K[1, 1] * x1 + K[1, 2]
+    return x
+
+
+# ----------------------------------------------------------------------------
 # evaluation metrics (utils.py:197-262, depth_train.py:522-527)
 # ----------------------------------------------------------------------------
 

@@ -218,3 +218,30 @@ def test_bn_totals_path_matches_slot_path(b2pose, dev, C, rows, relu, res):
            L.BF16, st)
     assert torch.equal(rm, a["rm"]) and torch.equal(mean2, mean3) and rel_err(invstd2, invstd3) < 1e-6
     assert rel_err(z2.float(), z3.float()) < 1e-2
+
+
+def test_head2d_and_projection(b2pose, dev, golden_dir):
+    """mat_utils.to_heatmap / decode (the D = 1 case of the head kernels) and
+    back_project.projectPoints against outputs of the reference's own functions."""
+    g = np.load(golden_dir + "/head2d.npz")
+    M = b2pose.mat_utils
+    for name in ("sq", "rect"):
+        cot = torch.tensor(g[f"{name}_cot"], device=dev)
+        for fused in (False, True):
+            feat = torch.tensor(g[f"{name}_feat"], device=dev, requires_grad=True)
+            N, J, H, W = feat.shape
+            if fused:
+                coords = M.heatmap_coords(feat, J, 257.0)
+            else:
+                heat = M.to_heatmap(feat, J, H, W)
+                assert tuple(heat.shape) == (N, J, H, W) and rel_err(heat, g[f"{name}_heat"]) < 1e-4
+                coords = M.decode(heat, 257.0)
+            (coords * cot).sum().backward()
+            assert tuple(coords.shape) == (N, J, 2)
+            assert float((coords.detach().cpu() - torch.tensor(g[f"{name}_coords"])).abs().max()) < 1e-2      # pixels
+            assert rel_err(coords, g[f"{name}_coords"]) < 1e-4 and rel_err(feat.grad, g[f"{name}_dfeat"]) < 1e-4
+    cam = dict(K=g["proj_K"], R=g["proj_R"], t=g["proj_t"], distCoef=g["proj_Kd"])
+    got = b2pose.back_project.projectPoints(g["proj_X"], cam)
+    np.testing.assert_allclose(got, g["proj_out"], rtol=2e-5, atol=1e-3)
+    got_t = b2pose.back_project.projectPoints(torch.tensor(g["proj_X"], device=dev, dtype=torch.float32), cam)
+    np.testing.assert_allclose(got_t.cpu().numpy(), g["proj_out"], rtol=2e-5, atol=1e-3)

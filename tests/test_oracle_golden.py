@@ -243,3 +243,18 @@ def test_metrics(golden_dir):
     ep = po.parse_epoch(stats)
     for k in keys[:-1]:
         np.testing.assert_allclose(ep[k], g[f"epoch_{k}"], rtol=1e-6)
+
+
+# ------------------------------------------------------------------ 2-D head + projection
+def test_head2d_and_projection(golden_dir):
+    g = load(golden_dir, "head2d")
+    for name in ("sq", "rect"):
+        feat = torch.tensor(g[f"{name}_feat"], requires_grad=True)
+        N, J, H, W = feat.shape
+        heat = po.mat_to_heatmap(feat, J, H, W)
+        coords = po.mat_decode(heat, 257.0)
+        (coords * torch.tensor(g[f"{name}_cot"])).sum().backward()
+        assert rel_err(heat.detach(), g[f"{name}_heat"]) < 1e-6 and rel_err(coords.detach(), g[f"{name}_coords"]) < 1e-6
+        assert rel_err(feat.grad, g[f"{name}_dfeat"]) < 1e-5
+    cam = dict(K=g["proj_K"], R=g["proj_R"], t=g["proj_t"], distCoef=g["proj_Kd"])
+    np.testing.assert_allclose(po.project_points(g["proj_X"], cam), g["proj_out"], rtol=1e-12)
