@@ -1046,7 +1046,8 @@ bool conv_tc_supported(const B2ConvDesc* d, int op) {
   if (is_stem(d)) return op == 0 || op == 2;                // im2col + GEMM; network inputs need no dgrad
   if (d->C % 8 != 0) return false;
   const bool one = (d->R == 1 && d->S == 1);
-  if (partial && !one && !premasked) return false;          // needs x*mask in the loader: CUDA-core path
+  if (partial && !one && !premasked && op != 1) return false;   // fprop / wgrad need x*mask in the loader (callers pre-mask);
+                                                                 // dgrad only scales its OUTPUT rows by the mask
   if (partial && one && d->stride != 1) return false;
   if (op == 0) return true;
   if (op == 1 && (d->flags & B2_CONV_DX_ACCUMULATE)) return d->stride == 1 && d->C % 64 == 0 && d->C <= 256 * 8;

@@ -311,6 +311,19 @@ class ConvFn(Function):
         b32 = None if bias is None else bias.detach().float().contiguous()
         if partial:
             mask = mask.contiguous()
+        ctx.self_masked = False
+        if partial and not premasked and not force_ffma and x.dtype == torch.bfloat16 and R * S > 1:
+            # The tensor-core kernels read x through TMA and cannot multiply by the mask on the way in: form x*mask
+            # once here (one streaming pass) and take the pre-masked path -- the CUDA-core kernel this replaces ran
+            # 20-40x slower than cuDNN on the isolated-layer sweep.  dgrad then scales its output rows by the mask.
+            desc.flags |= L.CONV_X_PREMASKED
+            if L.lib().b2_conv_uses_tensor_cores(C.byref(desc), 0):
+                xm = torch.empty_like(x)
+                L.call("b2_scale_rows", L.ptr(x), L.ptr(mask), L.ptr(xm), x.shape[0] * x.shape[1] * x.shape[2],
+                       x.shape[3], L.dt(x), L.stream())
+                x, ctx.self_masked = xm, True
+            else:
+                desc.flags &= ~L.CONV_X_PREMASKED
         y, mask_out, ratio, _ = _conv_fprop(desc, x, mask if partial else None, wk, b32, True, False)
         ctx.desc, ctx.has_bias, ctx.wdtype = desc, bias is not None, weight.dtype
         ctx.save_for_backward(x, mask if partial else None, wk, ratio, mask_out)
@@ -325,7 +338,13 @@ class ConvFn(Function):
         dy = dy.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _conv_dgrad(desc, dy, ratio, wk, mask)
+            if ctx.self_masked:                  # x was masked here, not by the producer: dx = dgrad(...) * mask
+                desc.flags &= ~L.CONV_X_PREMASKED
+            try:
+                dx = _conv_dgrad(desc, dy, ratio, wk, mask)
+            finally:
+                if ctx.self_masked:
+                    desc.flags |= L.CONV_X_PREMASKED
         if ctx.needs_input_grad[2]:
             dw = _conv_wgrad(desc, x, mask, dy, ratio).to(ctx.wdtype)
         if ctx.has_bias and ctx.needs_input_grad[3]:
