@@ -383,6 +383,17 @@ class ConvBNFn(Function):
         wk = filter_krsc(weight, x.dtype, shadow)
         if partial:
             mask = mask.contiguous()
+        ctx.self_masked = False
+        if partial and not premasked and not force_ffma and x.dtype == torch.bfloat16 and R * S > 1:
+            # un-premasked 3x3 PartialConv (first conv of a BasicBlock): form x*mask once and stay on the tensor cores
+            desc.flags |= L.CONV_X_PREMASKED
+            if L.lib().b2_conv_uses_tensor_cores(C.byref(desc), 0):
+                xm = torch.empty_like(x)
+                L.call("b2_scale_rows", L.ptr(x), L.ptr(mask), L.ptr(xm), x.shape[0] * x.shape[1] * x.shape[2],
+                       x.shape[3], L.dt(x), L.stream())
+                x, ctx.self_masked = xm, True
+            else:
+                desc.flags &= ~L.CONV_X_PREMASKED
         fast = bn_totals_supported(K, x.dtype)       # totals path: no finalize kernels
         y, mask_out, ratio, sums = _conv_fprop(desc, x, mask if partial else None, wk, None, True, training, fast)
         rows = desc.N * desc.Ho * desc.Wo
@@ -459,7 +470,13 @@ class ConvBNFn(Function):
                 dw = dw.to(ctx.wdtype)
         if ctx.needs_input_grad[0]:
             addend = ctx.dx_holder.pop("dres", None) if ctx.dx_holder is not None else None
-            dx = _conv_dgrad(desc, dy, None, wk, mask, addend)
+            if ctx.self_masked:                  # x was masked in this node: dgrad scales its rows by the mask
+                desc.flags &= ~L.CONV_X_PREMASKED
+            try:
+                dx = _conv_dgrad(desc, dy, None, wk, mask, addend)
+            finally:
+                if ctx.self_masked:
+                    desc.flags |= L.CONV_X_PREMASKED
         desc.flags &= ~L.CONV_DY_PRESCALED
         if sinks is not None:
             dgamma = dbeta = None
