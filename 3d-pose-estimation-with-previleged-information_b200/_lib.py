@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2pose.so")
 
 F32, BF16 = 0, 1
-CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA, CONV_DX_ACCUMULATE, CONV_BN_TOTALS = 1, 2, 4, 8, 16, 32
+CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA, CONV_DX_ACCUMULATE, CONV_BN_TOTALS, CONV_W_PREPARED = 1, 2, 4, 8, 16, 32, 64
 ABI_VERSION = 3
 BN_PARTS = 320
 MIMIC_PARTS = 64
@@ -34,6 +34,8 @@ SIGNATURES = {
     "b2_conv_workspace_bytes": [_D, _i],
     "b2_pconv_fprop": [_D, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p],
     "b2_pconv_dgrad": [_D, _p, _p, _p, _p, _p, _p, C.c_size_t, _p],
+    "b2_pconv_dgrad_filter_bytes": [_D],
+    "b2_pconv_dgrad_filter": [_D, _p, _p, C.c_size_t, _p],
     "b2_pconv_wgrad": [_D, _p, _p, _p, _p, _p, _p, C.c_size_t, _p],
     "b2_pconv_mask_update": [_D, _p, _p, _p, _p],
     "b2_scale_rows": [_p, _p, _p, _l, _i, _i, _p],
@@ -74,7 +76,8 @@ SIGNATURES = {
     "b2_adam_step": [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _f, _f, _p, _p],
     "b2_tc_selftest": [_p, _p, _p, _i, _i, _i, _i, _p],
 }
-_RESTYPE = {"b2_last_error": C.c_char_p, "b2_conv_workspace_bytes": C.c_size_t}
+_RESTYPE = {"b2_last_error": C.c_char_p, "b2_conv_workspace_bytes": C.c_size_t,
+            "b2_pconv_dgrad_filter_bytes": C.c_size_t}
 
 _lib = None
 launches = 0      # number of kernel-launching entry-point calls made through this binding

@@ -79,9 +79,25 @@ extern "C" int b2_pconv_dgrad(const B2ConvDesc* d, const void* dy, const float* 
     B2_REQUIRE(ws_bytes >= conv_tc_workspace_bytes(d, 1), B2_E_WORKSPACE, "pconv_dgrad: workspace too small");
     return conv_tc_dgrad(d, dy, ratio, w, mask_in, dx, workspace, st);
   }
+  B2_REQUIRE(!(d->flags & B2_CONV_W_PREPARED), B2_E_UNSUPPORTED,
+             "pconv_dgrad: B2_CONV_W_PREPARED needs the tensor-core path");
   B2_REQUIRE(!(d->flags & B2_CONV_DX_ACCUMULATE), B2_E_UNSUPPORTED,
              "pconv_dgrad: B2_CONV_DX_ACCUMULATE needs the bf16 tensor-core path (stride 1, C %% 64 == 0)");
   return conv_ffma_dgrad(d, dy, ratio, w, mask_in, dx, st);
+}
+
+extern "C" size_t b2_pconv_dgrad_filter_bytes(const B2ConvDesc* d) {
+  if (check_desc(d) != B2_OK || !use_tc(d, 1)) return 0;
+  return (size_t)d->K * d->R * d->S * d->C * 2;
+}
+
+extern "C" int b2_pconv_dgrad_filter(const B2ConvDesc* d, const void* w, void* wt, size_t wt_bytes, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  B2_REQUIRE(w && wt, B2_E_BADARG, "pconv_dgrad_filter: null tensor");
+  B2_REQUIRE(use_tc(d, 1), B2_E_UNSUPPORTED, "pconv_dgrad_filter: this dgrad does not run on the tensor-core path");
+  B2_REQUIRE(wt_bytes >= (size_t)d->K * d->R * d->S * d->C * 2, B2_E_WORKSPACE, "pconv_dgrad_filter: buffer too small");
+  return conv_tc_dgrad_filter(d, w, wt, (cudaStream_t)stream);
 }
 
 extern "C" int b2_pconv_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy,

@@ -1137,14 +1137,17 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   return B2_OK;
 }
 
-int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w, const float* mask_in,
-                  void* dx, void* workspace, cudaStream_t st) {
+// mode 0: transpose the filter into the workspace, then run; 1: ONLY the filter transposes, written to `workspace`
+// (b2_pconv_dgrad_filter: the weights are constant during a step, so callers hoist this off the backward critical
+// path); 2: `w` already is the buffer mode 1 produced (B2_CONV_W_PREPARED).
+static int conv_tc_dgrad_impl(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w,
+                              const float* mask_in, void* dx, void* workspace, cudaStream_t st, int mode) {
   const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
   uint8_t* ws = (uint8_t*)workspace;
-  bf16* wt = (bf16*)ws;
+  bf16* wt = mode == 2 ? (bf16*)const_cast<void*>(w) : (bf16*)ws;
   ws += align256((size_t)d->K * d->R * d->S * d->C * 2);
   const void* dys = dy;
-  if (partial && !(d->flags & B2_CONV_DY_PRESCALED) && ratio) {
+  if (mode != 1 && partial && !(d->flags & B2_CONV_DY_PRESCALED) && ratio) {
     int rc = b2_scale_rows(dy, ratio, ws, (int64_t)d->N * d->Ho * d->Wo, d->K, B2_BF16, (void*)st);
     if (rc) return rc;
     dys = ws;
@@ -1164,8 +1167,11 @@ int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const
     for (int r = 0; r < d->R; ++r)
       for (int s2 = 0; s2 < d->S; ++s2) tm.src[r * d->S + s2] = (d->R - 1 - r) * d->S + (d->S - 1 - s2);
     dim3 tg((d->C + 31) / 32, (d->K + 31) / 32, taps);
-    launch_pdl(tap_transpose_kernel, tg, tb, 0, st, (const bf16*)w, wt, d->K, d->C, taps, tm);
-    B2_LAUNCH_CHECK("tap_transpose");
+    if (mode != 2) {
+      launch_pdl(tap_transpose_kernel, tg, tb, 0, st, (const bf16*)w, wt, d->K, d->C, taps, tm);
+      B2_LAUNCH_CHECK("tap_transpose");
+    }
+    if (mode == 1) return B2_OK;
     a.filt = wt; a.R = d->R; a.S = d->S; a.dil = d->dil; a.pad = d->dil * (d->R - 1) - d->pad;
     a.Ho = d->H; a.Wo = d->W; a.out_stride_sp = 1;
     a.accumulate = (d->flags & B2_CONV_DX_ACCUMULATE) ? 1 : 0;
@@ -1182,7 +1188,7 @@ int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const
     for (int s2 = 0; s2 < d->S; ++s2) cs += (((ph + d->pad - s2) % sd + sd) % sd == 0);
     if (cr == 0 || cs == 0) need_zero = true;
   }
-  if (need_zero) {
+  if (need_zero && mode != 1) {
     cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->N * d->H * d->W * d->C * 2, st);
     B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc_dgrad: memset failed: %s", cudaGetErrorString(e));
   }
@@ -1202,8 +1208,11 @@ int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const
       for (int i = 0; i < nr; ++i)
         for (int j = 0; j < ns; ++j) tm.src[i * ns + j] = rl[i] * d->S + sl[j];
       dim3 tg((d->C + 31) / 32, (d->K + 31) / 32, tm.n);
-      launch_pdl(tap_transpose_kernel, tg, tb, 0, st, (const bf16*)w, wcls, d->K, d->C, taps, tm);
-      B2_LAUNCH_CHECK("tap_transpose");
+      if (mode != 2) {
+        launch_pdl(tap_transpose_kernel, tg, tb, 0, st, (const bf16*)w, wcls, d->K, d->C, taps, tm);
+        B2_LAUNCH_CHECK("tap_transpose");
+      }
+      if (mode == 1) { wcls += (size_t)tm.n * d->K * d->C; continue; }
       // floor division of (ph + pad - r_max) by the stride (exact by construction)
       auto fdiv = [](int a_, int b_) { return (a_ >= 0) ? a_ / b_ : -((-a_ + b_ - 1) / b_); };
       const int o0h = fdiv(ph + d->pad - rl[0], sd), o0w = fdiv(pw + d->pad - sl[0], sd);
@@ -1222,6 +1231,15 @@ int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const
     }
   }
   return B2_OK;
+}
+
+int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w, const float* mask_in,
+                  void* dx, void* workspace, cudaStream_t st) {
+  return conv_tc_dgrad_impl(d, dy, ratio, w, mask_in, dx, workspace, st, (d->flags & B2_CONV_W_PREPARED) ? 2 : 0);
+}
+
+int conv_tc_dgrad_filter(const B2ConvDesc* d, const void* w, void* wt, cudaStream_t st) {
+  return conv_tc_dgrad_impl(d, nullptr, nullptr, w, nullptr, nullptr, wt, st, 1);
 }
 
 int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy, const float* ratio,

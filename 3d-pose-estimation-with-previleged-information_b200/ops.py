@@ -234,10 +234,10 @@ def _conv_dgrad(desc, dy, ratio, wk, mask, addend=None):
 # reads is kept alive until the streams join (the caching allocator would otherwise hand its memory to
 # the main stream while the side stream still reads it); the side stream has its own scratch workspace.
 class _Overlap:
-    __slots__ = ("stream", "keep", "active", "main")
+    __slots__ = ("stream", "keep", "active", "main", "prepared")
 
     def __init__(self):
-        self.stream, self.keep, self.active, self.main = None, [], False, None
+        self.stream, self.keep, self.active, self.main, self.prepared = None, [], False, None, False
 
 
 _overlaps = {}
@@ -250,7 +250,34 @@ def wgrad_overlap_begin(device):
     o = _overlaps.setdefault(device.index, _Overlap())
     if o.stream is None:
         o.stream = torch.cuda.Stream(device=device)
-    o.keep, o.active, o.main = [], True, torch.cuda.current_stream(device)
+    o.keep, o.active, o.main, o.prepared = [], True, torch.cuda.current_stream(device), False
+
+
+def wgrad_overlap_sync(device):
+    """Forward / backward boundary: the filter transforms enqueued on the side stream during the forward pass
+    (`_prepare_dgrad_filter`) must be complete before the first dgrad."""
+    o = _overlaps.get(device.index)
+    if o is not None and o.active and o.prepared:
+        torch.cuda.current_stream(device).wait_stream(o.stream)
+        o.prepared = False
+
+
+def _prepare_dgrad_filter(desc, wk):
+    """The tensor-core dgrad reads the filter flipped / transposed.  Inside a managed step the transform runs on the
+    (otherwise idle) weight-gradient stream during the FORWARD pass, so the 86 small kernels leave the backward
+    critical path.  Returns the prepared buffer or None (not a managed step / no tensor-core dgrad)."""
+    o = _overlaps.get(wk.device.index)
+    if o is None or not o.active:
+        return None
+    nbytes = L.lib().b2_pconv_dgrad_filter_bytes(C.byref(desc))
+    if nbytes == 0:
+        return None
+    wt = torch.empty(nbytes, dtype=torch.uint8, device=wk.device)
+    o.stream.wait_stream(torch.cuda.current_stream(wk.device))      # wk (and the block behind wt) are ready
+    with torch.cuda.stream(o.stream):
+        L.call("b2_pconv_dgrad_filter", C.byref(desc), L.ptr(wk), L.ptr(wt), nbytes, L.stream())
+    o.prepared = True
+    return wt
 
 
 def wgrad_overlap_end(device):
@@ -418,6 +445,7 @@ class ConvBNFn(Function):
             L.call("b2_bn_apply", L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(gamma), L.ptr(beta), L.ptr(residual),
                    L.ptr(row_mask), int(relu), L.ptr(z), rows, K, L.dt(y), L.stream())
         ctx.fast = fast
+        ctx.wt = _prepare_dgrad_filter(desc, wk) if ctx.needs_input_grad[0] else None
         ctx.desc, ctx.relu, ctx.training, ctx.wdtype = desc, relu, training, weight.dtype
         ctx.has_res = residual is not None
         ctx.sinks = sinks
@@ -472,9 +500,13 @@ class ConvBNFn(Function):
             addend = ctx.dx_holder.pop("dres", None) if ctx.dx_holder is not None else None
             if ctx.self_masked:                  # x was masked in this node: dgrad scales its rows by the mask
                 desc.flags &= ~L.CONV_X_PREMASKED
+            wt = ctx.wt
+            if wt is not None:                   # filter transform done during the forward pass, off this path
+                desc.flags |= L.CONV_W_PREPARED
             try:
-                dx = _conv_dgrad(desc, dy, None, wk, mask, addend)
+                dx = _conv_dgrad(desc, dy, None, wk if wt is None else wt, mask, addend)
             finally:
+                desc.flags &= ~L.CONV_W_PREPARED
                 if ctx.self_masked:
                     desc.flags |= L.CONV_X_PREMASKED
         desc.flags &= ~L.CONV_DY_PRESCALED

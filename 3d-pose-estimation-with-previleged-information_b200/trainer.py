@@ -293,6 +293,7 @@ class Trainer:
                 loss, spec = self._forward_loss(*batch, semi=semi)
             else:
                 loss, spec = self._forward_loss(*batch)
+            ops.wgrad_overlap_sync(self.device)   # filter transforms prepared on the side stream during forward
             loss.backward()
         finally:
             ops.wgrad_overlap_end(self.device)

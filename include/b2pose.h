@@ -51,8 +51,10 @@ enum {
   B2_CONV_DX_ACCUMULATE = 16,/* dgrad: dx += result (bf16 TMA reduce-add) -- folds the gradient of */
                              /* a residual branch into the block input's gradient; tensor-core     */
                              /* path with stride 1 and C % 64 == 0 only, B2_E_UNSUPPORTED otherwise */
-  B2_CONV_BN_TOTALS = 32     /* fprop: bn_partials is ONE pre-zeroed float[2*K] the producer ADDS   */
+  B2_CONV_BN_TOTALS = 32,    /* fprop: bn_partials is ONE pre-zeroed float[2*K] the producer ADDS   */
                              /* to (totals BatchNorm path, needs b2_bn_totals_supported(K, dtype))  */
+  B2_CONV_W_PREPARED = 64    /* dgrad: `w` is the buffer b2_pconv_dgrad_filter produced for this     */
+                             /* descriptor (flipped / transposed filter), not the KRSC filter        */
 };
 
 typedef struct B2ConvDesc {
@@ -92,6 +94,13 @@ int b2_pconv_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, con
  * ratio / mask_in may be NULL (plain convolution). */
 int b2_pconv_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w,
                    const float* mask_in, void* dx, void* workspace, size_t ws_bytes, void* stream);
+
+/* The tensor-core dgrad reads the filter flipped and transposed ([C][taps][K], per output-parity class for strided
+ * layers).  The weights are constant during a training step, so the transform can be hoisted off the backward
+ * critical path: b2_pconv_dgrad_filter writes it to `wt` (b2_pconv_dgrad_filter_bytes(d) bytes, 0 = this dgrad does
+ * not run on the tensor-core path), and b2_pconv_dgrad with B2_CONV_W_PREPARED takes `wt` in place of `w`. */
+size_t b2_pconv_dgrad_filter_bytes(const B2ConvDesc* d);
+int b2_pconv_dgrad_filter(const B2ConvDesc* d, const void* w, void* wt, size_t wt_bytes, void* stream);
 
 /* backward w.r.t. w:  dw[K,R,S,C] (fp32, ACCUMULATED into) += wgrad(x*mask_in, dy*ratio). */
 int b2_pconv_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy,
