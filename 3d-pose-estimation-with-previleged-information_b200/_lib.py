@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libb2pose.so")
 
 F32, BF16 = 0, 1
 CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA, CONV_DX_ACCUMULATE, CONV_BN_TOTALS, CONV_W_PREPARED = 1, 2, 4, 8, 16, 32, 64
+CONV_WS_HAS_COL = 128
 ABI_VERSION = 3
 BN_PARTS = 320
 MIMIC_PARTS = 64

@@ -1273,8 +1273,10 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
     ws += align256((size_t)d->N * d->Ho * d->Wo * kpad * 2);
     dwp = (float*)ws;
     ws += align256((size_t)d->K * kpad * 4);
-    int rc = launch_im2col(d, x, (partial && !premasked) ? mask_in : nullptr, col, st);
-    if (rc) return rc;
+    if (!(d->flags & B2_CONV_WS_HAS_COL)) {       // (else: the caller kept the fprop workspace, the matrix is in it)
+      int rc = launch_im2col(d, x, (partial && !premasked) ? mask_in : nullptr, col, st);
+      if (rc) return rc;
+    }
     cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)d->K * kpad * 4, st);
     B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc_wgrad: memset failed: %s", cudaGetErrorString(e));
     x = col;

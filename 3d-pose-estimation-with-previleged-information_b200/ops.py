@@ -181,7 +181,7 @@ def veil_from_depth(depth_nhwc):
     return veil
 
 
-def _conv_fprop(desc, x, mask, wk, bias, want_ratio, want_stats, totals=False):
+def _conv_fprop(desc, x, mask, wk, bias, want_ratio, want_stats, totals=False, keep_ws=None):
     dev = x.device
     y = torch.empty((desc.N, desc.Ho, desc.Wo, desc.K), dtype=x.dtype, device=dev)
     partial = bool(desc.flags & L.CONV_PARTIAL)
@@ -190,7 +190,10 @@ def _conv_fprop(desc, x, mask, wk, bias, want_ratio, want_stats, totals=False):
     sums = None
     if want_stats:
         sums = bn_totals(desc.K, dev) if totals else bn_partials(desc.K, dev)
-    ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 0), dev)
+    if keep_ws is not None:        # stem layers in a training step: a private buffer whose im2col matrix wgrad reuses
+        ws, wsn = keep_ws, keep_ws.numel()
+    else:
+        ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 0), dev)
     if want_stats and totals:
         desc.flags |= L.CONV_BN_TOTALS
     try:
@@ -289,18 +292,18 @@ def wgrad_overlap_end(device):
     o.keep, o.active, o.main = [], False, None
 
 
-def _conv_wgrad(desc, x, mask, dy, ratio, sink=None):
+def _conv_wgrad(desc, x, mask, dy, ratio, sink=None, col_ws=None):
     o = _overlaps.get(dy.device.index)
     if o is None or not o.active or sink is None:
-        return _conv_wgrad_now(desc, x, mask, dy, ratio, sink, 0)
+        return _conv_wgrad_now(desc, x, mask, dy, ratio, sink, 0, col_ws)
     o.stream.wait_stream(torch.cuda.current_stream(dy.device))      # dy (and x) are ready
-    o.keep.append((x, mask, dy, ratio))
+    o.keep.append((x, mask, dy, ratio, col_ws))
     with torch.cuda.stream(o.stream):
-        _conv_wgrad_now(desc, x, mask, dy, ratio, sink, 1)
+        _conv_wgrad_now(desc, x, mask, dy, ratio, sink, 1, col_ws)
     return None
 
 
-def _conv_wgrad_now(desc, x, mask, dy, ratio, sink=None, ws_slot=0):
+def _conv_wgrad_now(desc, x, mask, dy, ratio, sink=None, ws_slot=0, col_ws=None):
     """dw (fp32, KRSC) accumulated into ``sink`` (a [K,C,R,S] channels_last view of the flat gradient
     buffer; returns None) or into a fresh zero tensor (returned as logical [K,C,R,S])."""
     dev = dy.device
@@ -310,9 +313,16 @@ def _conv_wgrad_now(desc, x, mask, dy, ratio, sink=None, ws_slot=0):
             raise RuntimeError("gradient sink must be an fp32 channels_last view")
     else:
         dw = torch.zeros((desc.K, desc.R, desc.S, desc.C), dtype=torch.float32, device=dev)
-    ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 2), dev, ws_slot)
-    L.call("b2_pconv_wgrad", C.byref(desc), L.ptr(x), L.ptr(mask), L.ptr(dy), L.ptr(ratio), L.ptr(dw),
-           L.ptr(ws), wsn, L.stream())
+    if col_ws is not None:         # the fprop's private workspace: its im2col matrix is still in it
+        desc.flags |= L.CONV_WS_HAS_COL
+        ws, wsn = col_ws, col_ws.numel()
+    else:
+        ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 2), dev, ws_slot)
+    try:
+        L.call("b2_pconv_wgrad", C.byref(desc), L.ptr(x), L.ptr(mask), L.ptr(dy), L.ptr(ratio), L.ptr(dw),
+               L.ptr(ws), wsn, L.stream())
+    finally:
+        desc.flags &= ~L.CONV_WS_HAS_COL
     return None if sink is not None else dw.permute(0, 3, 1, 2)
 
 
@@ -422,7 +432,13 @@ class ConvBNFn(Function):
             else:
                 desc.flags &= ~L.CONV_X_PREMASKED
         fast = bn_totals_supported(K, x.dtype)       # totals path: no finalize kernels
-        y, mask_out, ratio, sums = _conv_fprop(desc, x, mask if partial else None, wk, None, True, training, fast)
+        ctx.col_ws = None
+        if x.shape[3] <= 4 and ctx.needs_input_grad[2] and L.lib().b2_conv_uses_tensor_cores(C.byref(desc), 2):
+            # stem (im2col + GEMM): keep the workspace so that wgrad reuses the im2col matrix instead of rebuilding it
+            nb = max(L.lib().b2_conv_workspace_bytes(C.byref(desc), 0), L.lib().b2_conv_workspace_bytes(C.byref(desc), 2))
+            ctx.col_ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=x.device)
+        y, mask_out, ratio, sums = _conv_fprop(desc, x, mask if partial else None, wk, None, True, training, fast,
+                                               ctx.col_ws)
         rows = desc.N * desc.Ho * desc.Wo
         z = torch.empty_like(y)
         mean = torch.empty(K, dtype=torch.float32, device=x.device)
@@ -493,7 +509,7 @@ class ConvBNFn(Function):
         desc.flags |= L.CONV_DY_PRESCALED
         dx = dw = None
         if ctx.needs_input_grad[2]:        # first: on the side stream it then runs beside this layer's dgrad
-            dw = _conv_wgrad(desc, x, mask, dy, None, sinks[0] if sinks is not None else None)
+            dw = _conv_wgrad(desc, x, mask, dy, None, sinks[0] if sinks is not None else None, ctx.col_ws)
             if dw is not None:
                 dw = dw.to(ctx.wdtype)
         if ctx.needs_input_grad[0]:

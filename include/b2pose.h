@@ -53,8 +53,10 @@ enum {
                              /* path with stride 1 and C % 64 == 0 only, B2_E_UNSUPPORTED otherwise */
   B2_CONV_BN_TOTALS = 32,    /* fprop: bn_partials is ONE pre-zeroed float[2*K] the producer ADDS   */
                              /* to (totals BatchNorm path, needs b2_bn_totals_supported(K, dtype))  */
-  B2_CONV_W_PREPARED = 64    /* dgrad: `w` is the buffer b2_pconv_dgrad_filter produced for this     */
+  B2_CONV_W_PREPARED = 64,   /* dgrad: `w` is the buffer b2_pconv_dgrad_filter produced for this     */
                              /* descriptor (flipped / transposed filter), not the KRSC filter        */
+  B2_CONV_WS_HAS_COL = 128   /* wgrad of a stem layer (C <= 4): `workspace` is the very buffer the   */
+                             /* fprop of the same descriptor ran with, its im2col matrix is reused    */
 };
 
 typedef struct B2ConvDesc {
