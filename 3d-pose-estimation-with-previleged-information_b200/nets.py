@@ -44,9 +44,27 @@ class _Block(nn.Module):
         return {} if (self.downsample is None and torch.is_grad_enabled() and x.requires_grad) else None
 
     def _residual(self, x):
+        """Shortcut branch.  A down-sampling shortcut (1x1 conv + BN) runs on its own stream beside the block's main
+        path (forward here, backward through autograd's stream affinity); `_join` is called before it is consumed."""
+        self._side = None
         if self.downsample is None:
             return x
+        if ops.TWO_STREAMS and x.is_cuda:
+            cur, side = torch.cuda.current_stream(x.device), ops.shortcut_stream(x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                res, _ = conv_bn(x, None, self.downsample[0], self.downsample[1], relu=False)
+            self._side = (cur, side)
+            return res
         res, _ = conv_bn(x, None, self.downsample[0], self.downsample[1], relu=False)
+        return res
+
+    def _join(self, res):
+        if self._side is not None:
+            cur, side = self._side
+            cur.wait_stream(side)
+            res.record_stream(cur)
+            self._side = None
         return res
 
 
@@ -67,8 +85,8 @@ class BasicBlock(_Block):
     def forward_nhwc(self, x, veil):
         res, h = self._residual(x), self._holder(x)
         out, veil = conv_bn(x, veil, self.conv1, self.bn1, relu=True, mask_output=True, dx_holder=h)
-        out, veil = conv_bn(out, veil, self.conv2, self.bn2, relu=not self.skip_relu, residual=res, premasked=True,
-                            res_holder=h)
+        out, veil = conv_bn(out, veil, self.conv2, self.bn2, relu=not self.skip_relu, residual=self._join(res),
+                            premasked=True, res_holder=h)
         return out, veil
 
 
@@ -92,8 +110,8 @@ class Bottleneck(_Block):
         res, h = self._residual(x), self._holder(x)
         out, veil = conv_bn(x, veil, self.conv1, self.bn1, relu=True, mask_output=True, dx_holder=h)
         out, veil = conv_bn(out, veil, self.conv2, self.bn2, relu=True, mask_output=True, premasked=True)
-        out, veil = conv_bn(out, veil, self.conv3, self.bn3, relu=not self.skip_relu, residual=res, premasked=True,
-                            res_holder=h)
+        out, veil = conv_bn(out, veil, self.conv3, self.bn3, relu=not self.skip_relu, residual=self._join(res),
+                            premasked=True, res_holder=h)
         return out, veil
 
 

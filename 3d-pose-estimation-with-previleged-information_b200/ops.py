@@ -102,17 +102,32 @@ _branch_streams = {}
 TWO_STREAMS = __import__("os").environ.get("B2POSE_TWO_STREAMS", "1") != "0"
 
 
-def branch_stream(device):
-    st = _branch_streams.get(device.index)
+_stream_slots = {}          # (device index, cuda_stream handle) -> private workspace slot of an auxiliary stream
+
+
+def _aux_stream(device, name, slot):
+    key = (device.index, name)
+    st = _branch_streams.get(key)
     if st is None:
         st = torch.cuda.Stream(device=device)
-        _branch_streams[device.index] = st
+        _branch_streams[key] = st
+        _stream_slots[(device.index, st.cuda_stream)] = slot
     return st
 
 
-def _on_branch_stream(device):
-    st = _branch_streams.get(device.index)
-    return st is not None and torch.cuda.current_stream(device) == st
+def branch_stream(device):
+    return _aux_stream(device, "trunk", 2)
+
+
+def shortcut_stream(device):
+    """Stream for the down-sampling shortcut (1x1 conv + BN) of a block's first unit: it runs beside the block's
+    main path.  One per trunk: the shortcut of a block on the trunk stream gets its own."""
+    on_trunk = _stream_slots.get((device.index, torch.cuda.current_stream(device).cuda_stream)) == 2
+    return _aux_stream(device, "shortcut_b" if on_trunk else "shortcut_a", 4 if on_trunk else 3)
+
+
+def _aux_slot(device):
+    return _stream_slots.get((device.index, torch.cuda.current_stream(device).cuda_stream), 0)
 
 
 def workspace(nbytes, device, slot=0):
@@ -124,8 +139,8 @@ def workspace(nbytes, device, slot=0):
     any capture."""
     if nbytes == 0:
         return None, 0
-    if slot == 0 and _on_branch_stream(device):
-        slot = 2                     # the concurrent depth branch of the fusion nets has its own scratch
+    if slot == 0:
+        slot = _aux_slot(device)     # concurrent trunk / shortcut streams have their own scratch
     ws = _workspaces.get((device.index, slot))
     if ws is None or ws.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
