@@ -258,3 +258,30 @@ def test_head2d_and_projection(golden_dir):
         assert rel_err(feat.grad, g[f"{name}_dfeat"]) < 1e-5
     cam = dict(K=g["proj_K"], R=g["proj_R"], t=g["proj_t"], distCoef=g["proj_Kd"])
     np.testing.assert_allclose(po.project_points(g["proj_X"], cam), g["proj_out"], rtol=1e-12)
+
+
+# ------------------------------------------------------------------ property: the two partial-conv restatements agree
+def test_partial_conv_restatements_agree_on_random_geometry():
+    """The torch-op oracle (library convolution) and the explicit-loop oracle (no library) must agree on random
+    small geometries: ragged sizes, strides, dilations, all-invalid windows, with and without bias."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 2), st.integers(1, 3), st.integers(1, 4), st.integers(3, 9), st.integers(3, 9),
+           st.sampled_from([1, 3, 5]), st.integers(1, 2), st.integers(0, 2), st.integers(1, 2), st.booleans(),
+           st.floats(0.0, 1.0), st.integers(0, 10 ** 6))
+    def check(N, C, K, H, W, k, stride, pad, dil, with_bias, invalid, seed):
+        if H + 2 * pad - dil * (k - 1) < 1 or W + 2 * pad - dil * (k - 1) < 1:
+            return
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(N, C, H, W, generator=g)
+        mask = (torch.rand(N, 1, H, W, generator=g) >= invalid).float()
+        w = torch.randn(K, C, k, k, generator=g) * 0.3
+        b = torch.randn(K, generator=g) if with_bias else None
+        y, mo = po.partial_conv(x, mask, w, b, stride, pad, dil)
+        yl, ml = po.partial_conv_loops(x.numpy(), mask.numpy(), w.numpy(), None if b is None else b.numpy(), stride, pad, dil)
+        assert np.array_equal(mo.numpy(), ml)                       # updated masks bit-exact
+        np.testing.assert_allclose(y.numpy(), yl, rtol=2e-5, atol=2e-5)
+        assert np.all(y.numpy()[np.broadcast_to(ml == 0, y.shape)] == 0)      # all-invalid windows give exactly 0
+
+    check()
