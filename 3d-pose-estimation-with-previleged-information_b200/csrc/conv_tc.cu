@@ -160,7 +160,7 @@ struct FpropParams {
   int out_H, out_W;                                    // spatial size of the tensor written
   int tma_store;                                       // epilogue: smem-staged TMA store (+ fused BN statistics)
   int accumulate;                                      // TMA reduce-add into the output instead of a plain store
-  int debug;                                           // tuning experiments (B2POSE_TC_DEBUG): 1 skip epilogue, 2 skip store, 4 skip B reload
+  int debug;                                           // timing experiments (B2POSE_TC_DEBUG): 1 skip the epilogue body, 2 skip the TMA store, 4 skip the fused statistics
   float* bn_sums;                                      // partials[B2_BN_PARTS][2*K]: sum / sum of squares of the stored output
   int bn_totals;                                       // bn_sums is one pre-zeroed float[2*K]: add with fp32 reductions
 };
