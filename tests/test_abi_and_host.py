@@ -170,3 +170,23 @@ def test_bench_reference_arm_contract():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_host_side_helpers_against_golden(b2pose, golden_dir):
+    """Pure host logic of the widened surface: the float32 homography of the crop (cameralib.py:672-674) and
+    parse_epoch (utils.py:224-231) reproduce the fixtures produced by the reference, no GPU involved."""
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    for name in g["names"]:
+        hom = b2pose.pipeline.homography((g[f"{name}_K_old"], g[f"{name}_R_old"]), (g[f"{name}_K_new"], g[f"{name}_R_new"]))
+        assert hom.dtype == np.float32 and np.array_equal(hom, g[f"{name}_hom"])
+    m = np.load(os.path.join(golden_dir, "metrics.npz"))
+    keys = ("solid", "close", "depth", "jitter", "switch", "fail", "score_pck", "score_auc", "cam_mean", "batch_size")
+    stats = [{k: float(m[f"b{b}_{k}"]) for k in keys} for b in range(int(m["n_batches"]))]
+    ep = b2pose.parse_epoch(stats)
+    for k in keys[:-1]:
+        np.testing.assert_allclose(ep[k], float(m[f"epoch_{k}"]), rtol=1e-12)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        b2pose.pipeline.crop_enhance_depth(torch.zeros(1, 8, 8), None, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        b2pose.mimic_loss(torch.zeros(1, 4, 2, 2), torch.zeros(1, 4, 2, 2), torch.ones(1, 1, 2, 2))
