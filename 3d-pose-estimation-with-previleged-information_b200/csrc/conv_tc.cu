@@ -106,18 +106,113 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+// ---- MMA issue.  Measured with tools/mma_issue_probe.cu (profiles/r02_mma_issue_probe.md): one `tcgen05.mma` issued by
+// `if (lane == 0)` code costs ~73 cycles (ptxas wraps every instruction in an ELECT / BRA.U.ANY loop), and the issue
+// queue is shallow, so every mbarrier wait between two groups of MMAs (~170 cycles even when the barrier is already
+// complete) is a bubble in the tensor pipe: round 1's loop ran at 131-190 cycles per MMA whatever N.  One asm block
+// that (1) polls the barriers the NEXT group will need with the non-blocking `test_wait` (a `try_wait` on a phase that
+// is not complete yet suspends the warp in front of its own MMAs) -- the predicates are consumed only at the end of
+// the block, so the poll latency overlaps the issue -- and (2) issues four MMAs and the commits under ONE elect.sync predicate
+// runs at the floor: 55 / 64 / 128 cycles per MMA for N = 64 / 128 / 256.
+constexpr uint32_t kPoll1 = 1, kPoll2 = 2, kCommit1 = 4, kCommit2 = 8;
+// Four MMAs D[tmem_d] (+)= A_k * B_k, k = 0..3, descriptors advancing by `dstep` (encoded >> 4 units) per k-step.
+// acc0: accumulate flag of the first MMA (the others always accumulate).  Must be executed by a converged warp.
+__device__ __forceinline__ void mma4_fused(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint64_t dstep, uint32_t idesc,
+                                           uint32_t acc0, uint32_t flags, uint32_t poll1_bar, uint32_t poll1_parity,
+                                           uint32_t poll2_bar, uint32_t poll2_parity, uint32_t commit1_bar,
+                                           uint32_t commit2_bar, uint32_t& ready1, uint32_t& ready2) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t"
+      ".reg .pred pw1, pw2, pe, pa, q1, q2, c1, c2;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      ".reg .b32 t;\n\t"
+      "and.b32 t, %8, 1;\n\tsetp.ne.b32 q1, t, 0;\n\t"
+      "and.b32 t, %8, 2;\n\tsetp.ne.b32 q2, t, 0;\n\t"
+      "setp.ne.b32 pw1, 0, 0;\n\tsetp.ne.b32 pw2, 0, 0;\n\t"
+      "@q1 mbarrier.test_wait.parity.shared::cta.b64 pw1, [%9], %10;\n\t"
+      "@q2 mbarrier.test_wait.parity.shared::cta.b64 pw2, [%11], %12;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "and.b32 t, %8, 4;\n\tsetp.ne.b32 c1, t, 0;\n\tand.pred c1, c1, pe;\n\t"
+      "and.b32 t, %8, 8;\n\tsetp.ne.b32 c2, t, 0;\n\tand.pred c2, c2, pe;\n\t"
+      "setp.ne.b32 pa, %7, 0;\n\t"
+      "add.s64 a1, %3, %5;\n\tadd.s64 a2, a1, %5;\n\tadd.s64 a3, a2, %5;\n\t"
+      "add.s64 b1, %4, %5;\n\tadd.s64 b2, b1, %5;\n\tadd.s64 b3, b2, %5;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], %3, %4, %6, pa;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %6, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a2, b2, %6, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a3, b3, %6, 1;\n\t"
+      "@c1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t"
+      "@c2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%14];\n\t"
+      "selp.u32 %0, 1, 0, pw1;\n\tselp.u32 %1, 1, 0, pw2;\n\t"
+      "}"
+      : "=r"(ready1), "=r"(ready2)
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "l"(dstep), "r"(idesc), "r"(acc0), "r"(flags), "r"(poll1_bar),
+        "r"(poll1_parity), "r"(poll2_bar), "r"(poll2_parity), "r"(commit1_bar), "r"(commit2_bar)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+// Producer counterpart of mma4_fused: the single producing thread's serial latency per ring stage (a blocking wait on
+// `empty`, two integer divisions, two TMA issues wrapped in ELECT loops: ~400-600 cycles) bounded the shallow layers
+// once the MMA issue was fixed.  One asm block polls the NEXT stage's `empty` barrier (non-blocking, consumed at the
+// end) and issues expect_tx + the activation box (+ the filter slice when kLoadB) under one elect.sync predicate.
+constexpr uint32_t kLoadB = 2;
+__device__ __forceinline__ uint32_t produce_fused(uint32_t flags, uint32_t poll_bar, uint32_t poll_parity, uint32_t full_bar,
+                                                  uint32_t tx_bytes, uint32_t dst_a, const CUtensorMap* map_a, int a0, int a1,
+                                                  int a2, int a3, uint32_t dst_b, const CUtensorMap* map_b, int b0, int b1) {
+  uint32_t ready;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pw, pe, q, lb;\n\t"
+      ".reg .b32 t;\n\t"
+      "and.b32 t, %1, 1;\n\tsetp.ne.b32 q, t, 0;\n\t"
+      "setp.ne.b32 pw, 0, 0;\n\t"
+      "@q mbarrier.test_wait.parity.shared::cta.b64 pw, [%2], %3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "and.b32 t, %1, 2;\n\tsetp.ne.b32 lb, t, 0;\n\tand.pred lb, lb, pe;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %5;\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%6], [%7, {%8, %9, %10, %11}], [%4];\n\t"
+      "@lb cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%12], [%13, {%14, %15}], [%4];\n\t"
+      "selp.u32 %0, 1, 0, pw;\n\t"
+      "}"
+      : "=r"(ready)
+      : "r"(flags), "r"(poll_bar), "r"(poll_parity), "r"(full_bar), "r"(tx_bytes), "r"(dst_a), "l"(map_a), "r"(a0), "r"(a1),
+        "r"(a2), "r"(a3), "r"(dst_b), "l"(map_b), "r"(b0), "r"(b1)
+      : "memory");
+  return ready;
 }
+
+// wgrad producer stage: poll + expect_tx + the two dY atoms (k0, k0 + 64; 8 KB apart) + the first X atom.
+__device__ __forceinline__ uint32_t produce_wgrad_fused(uint32_t flags, uint32_t poll_bar, uint32_t poll_parity,
+                                                        uint32_t full_bar, uint32_t tx_bytes, uint32_t dst_dy,
+                                                        const CUtensorMap* map_dy, int k0, int ow0, int oh0, int n0,
+                                                        uint32_t dst_x, const CUtensorMap* map_x, int xc, int xw, int xh) {
+  uint32_t ready;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pw, pe, q;\n\t"
+      ".reg .b32 t, d1, k1;\n\t"
+      "and.b32 t, %1, 1;\n\tsetp.ne.b32 q, t, 0;\n\t"
+      "setp.ne.b32 pw, 0, 0;\n\t"
+      "@q mbarrier.test_wait.parity.shared::cta.b64 pw, [%2], %3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "add.u32 d1, %6, 8192;\n\tadd.s32 k1, %8, 64;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %5;\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%6], [%7, {%8, %9, %10, %11}], [%4];\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [d1], [%7, {k1, %9, %10, %11}], [%4];\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%12], [%13, {%14, %15, %16, %11}], [%4];\n\t"
+      "selp.u32 %0, 1, 0, pw;\n\t"
+      "}"
+      : "=r"(ready)
+      : "r"(flags), "r"(poll_bar), "r"(poll_parity), "r"(full_bar), "r"(tx_bytes), "r"(dst_dy), "l"(map_dy), "r"(k0),
+        "r"(ow0), "r"(oh0), "r"(n0), "r"(dst_x), "l"(map_x), "r"(xc), "r"(xw), "r"(xh)
+      : "memory");
+  return ready;
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(pred));
+  return pred;
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
@@ -160,7 +255,7 @@ struct FpropParams {
   int out_H, out_W;                                    // spatial size of the tensor written
   int tma_store;                                       // epilogue: smem-staged TMA store (+ fused BN statistics)
   int accumulate;                                      // TMA reduce-add into the output instead of a plain store
-  int debug;                                           // timing experiments (B2POSE_TC_DEBUG): 1 skip the epilogue body, 2 skip the TMA store, 4 skip the fused statistics
+  int debug;                                           // timing experiments (B2POSE_TC_DEBUG): 1 skip the epilogue body, 2 skip the TMA store, 4 skip the fused statistics, 8 no operand loads, 16 no filter loads
   float* bn_sums;                                      // partials[B2_BN_PARTS][2*K]: sum / sum of squares of the stored output
   int bn_totals;                                       // bn_sums is one pre-zeroed float[2*K]: add with fp32 reductions
 };
@@ -207,52 +302,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BNI) * kBlockK * 2;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int kt = tile % p.tiles_k, mt = tile / p.tiles_k;
-        const int wi = mt % p.tiles_w, hi = (mt / p.tiles_w) % p.tiles_h, ni = mt / (p.tiles_w * p.tiles_h);
-        const int iw0 = wi * p.BW * p.stride - p.pad_w, ih0 = hi * p.BH * p.stride - p.pad, n0 = ni * p.BNI;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-          const int r = tap / p.S, s = tap - r * p.S;
-          mbar_wait(&bars->empty[stage], phase ^ 1);
-          mbar_expect_tx(&bars->full[stage], a_box_bytes + b_bytes);
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          tma_load_4d(sa, &map_a, &bars->full[stage], cb * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, n0);
-          tma_load_2d(sa + kABytes, &map_b, &bars->full[stage], tap * p.C + cb * kBlockK, kt * p.BN);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    // Converged warp; elect.sync inside produce_fused picks the issuing lane.  No divisions in the loop: (tap row,
+    // tap column, channel block) advance as counters.
+    const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BNI) * kBlockK * 2;
+    int stage = 0;
+    uint32_t phase = 0, empty_ready = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int kt = tile % p.tiles_k, mt = tile / p.tiles_k;
+      const int wi = mt % p.tiles_w, hi = (mt / p.tiles_w) % p.tiles_h, ni = mt / (p.tiles_w * p.tiles_h);
+      const int iw0 = wi * p.BW * p.stride - p.pad_w, ih0 = hi * p.BH * p.stride - p.pad, n0 = ni * p.BNI;
+      const bool more_tiles = tile + (int)gridDim.x < total_tiles;
+      int r = 0, s = 0, cb = 0, bcol = 0;                 // bcol = tap * C + cb * 64
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        if (!empty_ready) mbar_wait(&bars->empty[stage], phase ^ 1);
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        if (p.debug & 24) {
+          empty_ready = 0;
+          if (lane == 0) {
+            if (p.debug & 8) {                     // timing experiment: no operand loads at all
+              mbar_arrive(&bars->full[stage]);
+            } else {                               // timing experiment: activation tile only (filter "resident")
+              mbar_expect_tx(&bars->full[stage], a_box_bytes);
+              tma_load_4d(sa, &map_a, &bars->full[stage], cb * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, n0);
+            }
+          }
+          __syncwarp();
+        } else {
+          const bool has_next = kb + 1 < p.kblocks || more_tiles;
+          empty_ready = produce_fused((has_next ? 1u : 0u) | kLoadB, smem_u32(&bars->empty[nstage]), nphase ^ 1,
+                                      smem_u32(&bars->full[stage]), a_box_bytes + b_bytes, sa, &map_a, cb * kBlockK,
+                                      iw0 + s * p.dil, ih0 + r * p.dil, n0, sa + kABytes, &map_b, bcol, kt * p.BN);
         }
+        bcol += kBlockK;
+        if (++cb == p.cblocks) {
+          cb = 0;
+          bcol += p.C - p.cblocks * kBlockK;       // ragged last channel block: the next tap starts at tap * C
+          if (++s == p.S) { s = 0; ++r; }
+        }
+        stage = nstage;
+        phase = nphase;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The whole warp stays converged (elect.sync inside mma4_fused picks the issuing lane).  Every group of four MMAs
+    // polls the barrier the next group needs (`full` of the next ring stage, or the `tempty` of the next tile's
+    // accumulator when this is a tile's last k-block), so the blocking waits below normally fall through.
     const uint32_t idesc = instr_desc(kTileM, p.BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
+    uint32_t full_ready = 0, acc_ready = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&bars->tempty[acc], acc_phase ^ 1);
+      if (!acc_ready) mbar_wait(&bars->tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+      const bool more_tiles = tile + (int)gridDim.x < total_tiles;
+      const int nacc = (local + 1) & 1;
+      const uint32_t nacc_parity = (((local + 1) >> 1) & 1) ^ 1;
       for (int kb = 0; kb < p.kblocks; ++kb) {
-        mbar_wait(&bars->full[stage], phase);
+        if (!full_ready) mbar_wait(&bars->full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = smem_desc(sa, 0, 1024), bdesc = smem_desc(sa + kABytes, 0, 1024);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(kb | k));
-          umma_commit(&bars->empty[stage]);
-          if (kb == p.kblocks - 1) umma_commit(&bars->tfull[acc]);
-        }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+        const bool last = kb == p.kblocks - 1;
+        const uint32_t flags = ((!last || more_tiles) ? kPoll1 : 0u) | ((last && more_tiles) ? kPoll2 : 0u) | kCommit1 |
+                               (last ? kCommit2 : 0u);
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        mma4_fused(tmem_d, smem_desc(sa, 0, 1024), smem_desc(sa + kABytes, 0, 1024), 2ull, idesc, (uint32_t)kb, flags,
+                   smem_u32(&bars->full[nstage]), nphase, smem_u32(&bars->tempty[nacc]), nacc_parity,
+                   smem_u32(&bars->empty[stage]), smem_u32(&bars->tfull[acc]), full_ready, acc_ready);
+        stage = nstage;
+        phase = nphase;
       }
     }
   } else {
@@ -543,40 +670,61 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        int sp, tg, ct, kt;
-        decode(item, sp, tg, ct, kt);
-        const int tap0 = tg * p.T, nt = min(p.T, taps - tap0);
-        const int b0 = sp * p.bricks_per_split;
-        const int b1 = min(total_bricks, b0 + p.bricks_per_split);
-        for (int b = b0; b < b1; ++b) {
-          const int wi = b % p.tiles_w, hi = (b / p.tiles_w) % p.tiles_h, ni = b / (p.tiles_w * p.tiles_h);
-          const int ow0 = wi * p.BW, oh0 = hi * p.BH, n0 = ni * p.BNI;
-          mbar_wait(&bars->empty[stage], phase ^ 1);
-          mbar_expect_tx(&bars->full[stage], a_bytes + (uint32_t)nt * b_bytes);
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          // dy atoms: k channels [kt*128, +64) and [+64, +128)
-          tma_load_4d(sa, &map_dy, &bars->full[stage], kt * 128, ow0, oh0, n0);
-          tma_load_4d(sa + atom_bytes, &map_dy, &bars->full[stage], kt * 128 + 64, ow0, oh0, n0);
-          for (int j = 0; j < nt; ++j) {
-            const int tap = tap0 + j, r = tap / p.S, s = tap - r * p.S;
-            for (int a = 0; a < p.BNc / 64; ++a)
-              tma_load_4d(sa + a_bytes + j * b_bytes + a * atom_bytes, &map_x, &bars->full[stage],
-                          ct * p.BNc + a * 64, ow0 * p.stride - p.pad + s * p.dil,
-                          oh0 * p.stride - p.pad + r * p.dil, n0);
+    // TMA producer: converged warp (elect.sync picks the issuing lane), brick coordinates advance as counters, the
+    // next stage's `empty` barrier is polled while this stage's loads are issued (see produce_fused).
+    static_assert(kWgPix * 128 == 8192, "produce_wgrad_fused assumes 8 KB atoms");
+    int stage = 0;
+    uint32_t phase = 0, empty_ready = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int sp, tg, ct, kt;
+      decode(item, sp, tg, ct, kt);
+      const int tap0 = tg * p.T, nt = min(p.T, taps - tap0);
+      const int b0 = sp * p.bricks_per_split;
+      const int b1 = min(total_bricks, b0 + p.bricks_per_split);
+      const bool more_items = item + (int)gridDim.x < total_items;
+      int wi = b0 % p.tiles_w, hi = (b0 / p.tiles_w) % p.tiles_h, ni = b0 / (p.tiles_w * p.tiles_h);
+      const int r0 = tap0 / p.S, s0 = tap0 - r0 * p.S;
+      const int atoms = p.BNc / 64;
+      for (int b = b0; b < b1; ++b) {
+        const int ow0 = wi * p.BW, oh0 = hi * p.BH, n0 = ni * p.BNI;
+        if (!empty_ready) mbar_wait(&bars->empty[stage], phase ^ 1);
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t fb = smem_u32(&bars->full[stage]);
+        const int xw0 = ow0 * p.stride - p.pad, xh0 = oh0 * p.stride - p.pad;
+        const bool has_next = b + 1 < b1 || more_items;
+        // dy atoms: k channels [kt*128, +64) and [+64, +128); first x atom of the first tap
+        empty_ready = produce_wgrad_fused(has_next ? 1u : 0u, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
+                                          a_bytes + (uint32_t)nt * b_bytes, sa, &map_dy, kt * 128, ow0, oh0, n0,
+                                          sa + a_bytes, &map_x, ct * p.BNc, xw0 + s0 * p.dil, xh0 + r0 * p.dil);
+        if (nt * atoms > 1) {
+          if (elect_one()) {
+            int r = r0, s = s0;
+            for (int j = 0; j < nt; ++j) {
+              for (int a = (j == 0 ? 1 : 0); a < atoms; ++a)
+                tma_load_4d(sa + a_bytes + j * b_bytes + a * atom_bytes, &map_x, &bars->full[stage], ct * p.BNc + a * 64,
+                            xw0 + s * p.dil, xh0 + r * p.dil, n0);
+              if (++s == p.S) { s = 0; ++r; }
+            }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          __syncwarp();
         }
+        if (++wi == p.tiles_w) { wi = 0; if (++hi == p.tiles_h) { hi = 0; ++ni; } }
+        stage = nstage;
+        phase = nphase;
       }
     }
   } else if (warp == 1) {
+    // MMA issuer: converged warp, one fused asm block per tap (see mma4_fused); the first tap's block polls the next
+    // stage's `full` barrier (and the next item's accumulator when this is the item's last brick), the last tap's
+    // block commits.
     const uint32_t idesc = instr_desc(kTileM, p.BNc, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
+    uint32_t full_ready = 0, acc_ready = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++local) {
       int sp, tg, ct, kt;
       decode(item, sp, tg, ct, kt);
@@ -585,28 +733,38 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       const int b1 = min(total_bricks, b0 + p.bricks_per_split);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&bars->tempty[acc], acc_phase ^ 1);
+      if (!acc_ready) mbar_wait(&bars->tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+      const bool more_items = item + (int)gridDim.x < total_items;
+      const int nacc = (local + 1) & 1;
+      const uint32_t nacc_parity = (((local + 1) >> 1) & 1) ^ 1;
       for (int b = b0; b < b1; ++b) {
-        mbar_wait(&bars->full[stage], phase);
+        if (!full_ready) mbar_wait(&bars->full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          // MN-major, 128B swizzle: LBO = bytes between 64-element atoms along M/N, SBO = 1024 (8 pixel rows)
-          const uint64_t adesc = smem_desc(sa, atom_bytes, 1024);
-          for (int j = 0; j < nt; ++j) {
-            const uint64_t bdesc = smem_desc(sa + a_bytes + j * b_bytes, atom_bytes, 1024);
-#pragma unroll
-            for (int k = 0; k < kWgPix / 16; ++k)      // 16 pixels per MMA = 2 swizzle row groups = 2048 B
-              umma_bf16(tmem_d + (uint32_t)(j * p.BNc), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128),
-                        idesc, (uint32_t)((b - b0) | k));
-          }
-          umma_commit(&bars->empty[stage]);
-          if (b == b1 - 1) umma_commit(&bars->tfull[acc]);
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+        const bool last = b == b1 - 1;
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        // MN-major, 128B swizzle: LBO = bytes between 64-element atoms along M/N, SBO = 1024 (8 pixel rows);
+        // 16 pixels per MMA = 2 swizzle row groups = 2048 B = descriptor step 128
+        const uint64_t adesc = smem_desc(sa, atom_bytes, 1024);
+        uint32_t r1 = 0, r2 = 0;
+        for (int j = 0; j < nt; ++j) {
+          uint32_t flags = 0, q1, q2;
+          if (j == 0) flags |= ((!last || more_items) ? kPoll1 : 0u) | ((last && more_items) ? kPoll2 : 0u);
+          if (j == nt - 1) flags |= kCommit1 | (last ? kCommit2 : 0u);
+          mma4_fused(tmem_d + (uint32_t)(j * p.BNc), adesc, smem_desc(sa + a_bytes + j * b_bytes, atom_bytes, 1024), 128ull,
+                     idesc, (uint32_t)(b - b0), flags, smem_u32(&bars->full[nstage]), nphase,
+                     smem_u32(&bars->tempty[nacc]), nacc_parity, smem_u32(&bars->empty[stage]),
+                     smem_u32(&bars->tfull[acc]), q1, q2);
+          if (j == 0) { r1 = q1; r2 = q2; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        full_ready = r1;
+        acc_ready = r2;
+        stage = nstage;
+        phase = nphase;
       }
     }
   } else {
