@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libb2pose.so")
 F32, BF16 = 0, 1
 CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA, CONV_DX_ACCUMULATE, CONV_BN_TOTALS, CONV_W_PREPARED = 1, 2, 4, 8, 16, 32, 64
 CONV_WS_HAS_COL = 128
-ABI_VERSION = 3
+ABI_VERSION = 4
 BN_PARTS = 320
 MIMIC_PARTS = 64
 
@@ -75,7 +75,6 @@ SIGNATURES = {
     "b2_unproject_depth": [_p, _p, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p],
     "b2_grad_sumsq": [_p, _l, _p, _p],
     "b2_adam_step": [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _f, _f, _p, _p],
-    "b2_tc_selftest": [_p, _p, _p, _i, _i, _i, _i, _p],
 }
 _RESTYPE = {"b2_last_error": C.c_char_p, "b2_conv_workspace_bytes": C.c_size_t,
             "b2_pconv_dgrad_filter_bytes": C.c_size_t}

@@ -459,12 +459,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         epi_barrier();
         // software-pipelined TMEM reads: the loads of group g+1 are in flight while group g is converted.
         // The epilogue is instruction-issue bound on the shallow layers (8 warps on 4 schedulers), so the
-        // conversion uses packed fp32x2 multiplies and skips the multiply when there is no row scale:
-        // out-of-range rows of a ragged tile are zero in TMEM already (TMA zero-fills the A operand) and
-        // clipped by the TMA store.
+        // conversion uses packed fp32x2 multiplies and skips the multiply when there is no row scale.
+        // Out-of-range rows of a ragged tile are clipped by the TMA store but NOT zero in TMEM for R, S > 1 (output
+        // row Ho reads the valid input row Ho - 1 through tap r = 0), and the fused BatchNorm statistics below read the
+        // staged tile: such rows take the multiply path with scale 0 (round 1 skipped it and polluted the statistics
+        // of plain 3x3 layers whose output is not a multiple of the brick, e.g. every 257x257 configuration).
         const float sc = valid ? scale : 0.f;
         const uint64_t sc2 = pack2(sc, sc);
-        const bool unit = p.scale_mode == 0;
+        const bool unit = p.scale_mode == 0 && valid;
         uint32_t va[32], vb[32];
         tmem_ld16(taddr + half * 32, va);
         tmem_ld16(taddr + half * 32 + 16, va + 16);
@@ -1522,13 +1524,4 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
     B2_LAUNCH_CHECK("unpad_add");
   }
   return B2_OK;
-}
-
-// Debug entry kept for ABI stability: the tensor-core path is exercised through the convolution
-// entry points (tests/test_gpu_tc.py).
-extern "C" int b2_tc_selftest(const void* a, const void* b, float* c, int32_t M, int32_t N, int32_t K, int32_t variant,
-                              void* stream) {
-  (void)a; (void)b; (void)c; (void)M; (void)N; (void)K; (void)variant; (void)stream;
-  b2_set_error("tc_selftest: use the convolution entry points with bf16 tensors (tests/test_gpu_tc.py)");
-  return B2_E_UNSUPPORTED;
 }

@@ -115,8 +115,12 @@ def conv_bn(x, veil, conv, bn, relu, residual=None, mask_output=False, premasked
     """conv -> bn (+residual) (+relu) (*veil) on NHWC tensors; returns (z, veil_out)."""
     partial = isinstance(conv, PartialConv)
     training = bn.training
+    if bn.momentum is None:
+        # nn.BatchNorm2d(momentum=None) is a cumulative moving average (factor 1/num_batches_tracked); no reference
+        # net uses it and the fused kernels take one constant factor
+        raise NotImplementedError("b2pose BatchNorm2d needs a numeric momentum (cumulative averaging is not built)")
     cfg = (conv._s, conv._p, conv._d, partial, premasked and partial, relu, mask_output and partial, training,
-           0.1 if bn.momentum is None else bn.momentum, bn.eps, conv.force_ffma)
+           bn.momentum, bn.eps, conv.force_ffma)
     sinks = None
     if conv._grad_sink is not None and bn._grad_sinks is not None and torch.is_grad_enabled():
         sinks = (conv._grad_sink,) + bn._grad_sinks

@@ -28,6 +28,7 @@ def make_desc(xshape, K, R, S, stride, pad, dil, dtype, flags):
 
 
 _workspaces = {}
+_retired_workspaces = []      # replaced scratch buffers: captured CUDA graphs keep raw pointers into them
 
 
 def bn_partials(C, device):
@@ -136,7 +137,9 @@ def workspace(nbytes, device, slot=0):
     stream is the capture stream, and a buffer first allocated there would live in that graph's private
     memory pool -- a second graph (another Trainer in the same process) reusing it after the first
     graph was destroyed faulted.  The Trainer's eager warm-up steps grow it to its final size before
-    any capture."""
+    any capture.  A buffer that has to grow AFTER a capture (an evaluation batch between training steps, a
+    larger batch shape) is retired, not freed: replays of the captured graphs still write through its
+    address (same policy as `_Arena.retired`)."""
     if nbytes == 0:
         return None, 0
     if slot == 0:
@@ -146,6 +149,8 @@ def workspace(nbytes, device, slot=0):
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("libb2pose workspace would have to grow during CUDA-graph capture; run the "
                                "same shapes eagerly once before capturing")
+        if ws is not None:
+            _retired_workspaces.append(ws)
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[(device.index, slot)] = ws
     return ws, ws.numel()

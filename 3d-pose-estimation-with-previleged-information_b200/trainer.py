@@ -12,8 +12,13 @@ B200-first differences from the reference loop (results identical within toleran
   * the whole step (zero-grad, forward, head, loss, backward, clip, Adam) is captured in a CUDA
     graph and replayed; the learning rate and Adam bias corrections are read from a small device
     buffer so the schedule moves without re-capture;
-  * one process per GPU; gradients are averaged over ranks (DataParallel's gather-then-mean loss is
-    the same thing), BN statistics stay per rank like DataParallel's per-replica BN.
+  * one process per GPU; every rank takes the masked mean over ITS valid joints and the gradients are averaged over
+    ranks.  DataParallel's loss is the mean over the valid joints of the gathered batch, so the two agree exactly when
+    every rank holds the same number of valid joints and differ by the ratio cnt_rank / mean(cnt) otherwise (documented
+    deviation: no extra collective for the count); BN statistics stay per rank like DataParallel's per-replica BN;
+  * the Adam bias-correction step advances on steps the fused kernel skips for non-finite gradients, whereas the
+    reference does not call optimizer.step() there (:435-438); with bf16 + fp32 masters this only matters after a
+    genuine overflow.
 """
 import math
 from types import SimpleNamespace
@@ -156,6 +161,9 @@ class Trainer:
         self.list_names = [n for n, _ in model.named_parameters()]
         self.flat = _FlatState(model, want_shadow=self.half_acc)
         self.list_params = self.flat.params
+        # weights loaded from outside (model.load_state_dict) land in the fp32 flat buffer through the re-pointed
+        # parameters; the bf16 shadow filters the kernels read must follow
+        model.register_load_state_dict_post_hook(lambda module, incompatible: self.flat.refresh_shadow())
         self.bns = [m for m in model.modules() if isinstance(m, BatchNorm2d)]
         for m in self.bns:
             m.defer_count = True
@@ -324,6 +332,13 @@ class Trainer:
         ev.record()
         self._hyper_ring[slot] = (host, ev)
 
+    def _mode_key(self):
+        """Everything a captured step bakes in besides the batch shapes: replaying a graph captured under other
+        BatchNorm modes or hyper-parameters would silently run the stale configuration."""
+        return (tuple(m.training for m in self.bns), self.model.training, self.criterion, float(self.weight_decay),
+                float(self.grad_norm), self.betas, float(self.eps), float(self.loss_div), float(self.depth_range),
+                self.teacher is not None, self.sigmoid, self.bin_dist, self.world)
+
     def _buffers(self, table, batch):
         key = tuple(tuple(t.shape) for t in batch)
         st = table.get(key)
@@ -399,6 +414,7 @@ class Trainer:
             self._update()
             self.launches_per_step = L.launches - n0
         else:
+            key = (key, self._mode_key())
             entry = self._graphs.get(key)
             if entry is None:
                 entry = self._capture(key, st)

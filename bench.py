@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Benchmark of the depth-stream hot path: training samples/s of the two-stream ResNet-50
-(BASELINE.json configs[1]: fusionnet, batch 64 per GPU, bf16, synthetic 256x256 RGB + depth +
-validity holes) -- forward, head, loss, backward, clip-norm, Adam -- on N B200s of one node.
+"""Benchmark of the depth-stream hot path: training samples/s of the two-stream PartialConv ResNet-50
+(BASELINE.json configs[2] shape at north_star's 256x256 / J=17: partial_fusionnet with the fixed stems, batch 64 per
+GPU, bf16, synthetic RGB + depth + validity holes) -- forward, head, loss, backward, clip-norm, Adam -- on N B200s of
+one node.  `--workload fusionnet` selects configs[1] (plain two-stream net, no PartialConv layers).
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -10,7 +11,8 @@ validity holes) -- forward, head, loss, backward, clip-norm, Adam -- on N B200s 
 Prints ONE JSON line (rank 0).  `value` times K steps with the batch resident in HBM; `e2e`
 times K steps through Trainer.train_step with pinned HOST batches (H2D inside, loss read back
 every step); `roofline` times the dominant convolution kernel alone with CUDA events;
-`cpu_baseline` is the CPU oracle (a port of the reference step) on a bounded sample.
+`cpu_baseline` is the reference's own modules (imported unmodified from baseline/_ref) stepped on the host cores
+on a bounded sample; `gpu_eager_baseline` the same imported modules on this B200 in eager PyTorch (cuDNN).
 """
 import argparse
 import json
@@ -42,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="fusionnet", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="partial_fusionnet", choices=sorted(WORKLOADS))
     ap.add_argument("--model", default="resnet50")
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
     ap.add_argument("--side", type=int, default=256)
@@ -51,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the CPU baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch reference on the GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also write the per-layer kernel table to profiles/")
     return ap.parse_args()
@@ -104,29 +107,97 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-# ----------------------------------------------------------------------------- CPU arm (oracle port)
+# ----------------------------------------------------------------------------- reference arms
+def _ref_cfg(args):
+    from types import SimpleNamespace
+    wl = WORKLOADS[args.workload]
+    return SimpleNamespace(stride=16, depth=16, num_joints=args.joints, side_in=args.side, depth_only=not wl["fused"],
+                           early_dist=False, skip_relu=False, extra_channel=False, joint_space=False, pretrain=False)
+
+
+def _host_batch(args, batch, seed=1):
+    """The same synthetic batch generator the product arm uses (b2pose.synthetic_batch), on the host."""
+    import __graft_entry__ as ge
+    b2 = ge.load_package()
+    return b2.synthetic_batch(batch, args.side, args.joints, None, seed=seed, invalid_frac=0.25)
+
+
 def cpu_step_rate(args, steps, warmup, batch):
-    """The reference training step restated on CPU (oracle/pose_oracle.py StepOracle: imported
-    nowhere else in the product) on all host threads; returns (samples/s, cores, description)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    """The reference training step on the host cores, all threads.  The reference's own modules
+    (partial_fusionnet.py / utils.py ..., imported unmodified from baseline/_ref) when they are staged --
+    kind "reference" -- else the oracle port (oracle/pose_oracle.py StepOracle) -- kind "port".
+    Returns (samples/s, cores, description, ms per step, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
     import torch
-    import pose_oracle as po
+    import ref_step
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     wl = WORKLOADS[args.workload]
-    cfg = po.net_config(side_in=args.side, num_joints=args.joints)
-    sd = po.init_state(wl["kind"], args.model, cfg, seed=0)
-    orc = po.StepOracle(sd, wl["kind"], args.model, cfg, key_index=args.joints - 1)
-    data = po.synth_batch(batch, args.side, args.joints, seed=1, invalid_frac=0.25)
+    if ref_step.available():
+        ref = ref_step.import_reference()
+        torch.manual_seed(0)
+        orc = ref_step.RefStep(ref, wl["kind"], args.model, _ref_cfg(args), torch.device("cpu"), args.joints - 1)
+        data = _host_batch(args, batch)
+        kind = "reference"
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pose_oracle as po
+        cfg = po.net_config(side_in=args.side, num_joints=args.joints)
+        sd = po.init_state(wl["kind"], args.model, cfg, seed=0)
+        orc = po.StepOracle(sd, wl["kind"], args.model, cfg, key_index=args.joints - 1)
+        data = po.synth_batch(batch, args.side, args.joints, seed=1, invalid_frac=0.25)
+        kind = "port"
     for _ in range(warmup):
         orc.step(data)
     t0 = time.perf_counter()
     for _ in range(steps):
         orc.step(data)
     dt = time.perf_counter() - t0
-    sample = "%d steps of batch %d (fp32, %s %s %dx%d J=%d) after %d warm-up" % (
-        steps, batch, wl["kind"], args.model, args.side, args.side, args.joints, warmup)
-    return batch * steps / dt, cores, sample, dt / steps * 1e3
+    sample = "%d steps of batch %d (fp32, %s %s %dx%d J=%d, %s) after %d warm-up" % (
+        steps, batch, wl["kind"], args.model, args.side, args.side, args.joints,
+        "reference modules imported from baseline/_ref" if kind == "reference" else "oracle port", warmup)
+    return batch * steps / dt, cores, sample, dt / steps * 1e3, kind
+
+
+def gpu_eager_rates(args, dev, steps=5, warmup=2):
+    """BASELINE.md section 4's "bar to beat": the reference's own modules in eager PyTorch (cuDNN / ATen) on this
+    B200, same workload and per-GPU batch, forward + head + loss + backward + clip + Adam per step, batch resident
+    in HBM, CUDA events.  Variants: fp32 as shipped (NCHW), bf16 autocast NCHW, bf16 autocast channels_last."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import torch
+    import ref_step
+    if not ref_step.available():
+        return {"unavailable": "baseline/_ref is not staged (run python baseline/stage_reference.py where /root/reference exists)"}
+    ref = ref_step.import_reference()
+    wl = WORKLOADS[args.workload]
+    data = tuple(t.to(dev) for t in _host_batch(args, args.batch))
+    out = {"unit": UNIT, "batch": args.batch, "steps": steps, "warmup": warmup,
+           "what": "reference modules imported unmodified from baseline/_ref (partial_fusionnet with the documented "
+                   "2-line stem fix), eager PyTorch %s on this GPU, step = depth_train.py:384-456" % torch.__version__}
+    variants = (("fp32_nchw", None, False), ("bf16_autocast_nchw", torch.bfloat16, False),
+                ("bf16_autocast_channels_last", torch.bfloat16, True))
+    for name, ac, cl in variants:
+        try:
+            torch.manual_seed(0)
+            st = ref_step.RefStep(ref, wl["kind"], args.model, _ref_cfg(args), dev, args.joints - 1, autocast=ac,
+                                  channels_last=cl)
+            for _ in range(warmup):
+                st.step(data)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                loss = st.step(data)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": args.batch / ms * 1e3, "ms_per_step": ms, "loss": float(loss)}
+        except Exception as e:      # noqa: BLE001  (a variant the stock code cannot run is reported, not fatal)
+            out[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        finally:
+            st = None
+            torch.cuda.empty_cache()
+    return out
 
 
 def workload_config(args, world):
@@ -143,15 +214,16 @@ def run_reference(args):
     steps, warm = max(1, args.steps), max(1, min(args.warmup, 2))
     # bounded: a step of batch 8 takes ~2-4 s on the box's cores; cap total work at a few minutes
     steps = min(steps, 12)
-    value, cores, sample, ms = cpu_step_rate(args, steps, warm, args.cpu_batch)
-    wl = WORKLOADS[args.workload]
+    value, cores, sample, ms, kind = cpu_step_rate(args, steps, warm, args.cpu_batch)
+    how = ("the reference's own modules imported unmodified from baseline/_ref" if kind == "reference"
+           else "oracle port of the reference step")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args, args.gpus), sample="CPU (oracle port of the reference step, fp32, all host "
-                       "threads): each step = one batch of %d of the same workload" % args.cpu_batch),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": dict(workload_config(args, args.gpus), sample="CPU (%s, fp32, all host threads): each step = one "
+                       "batch of %d of the same workload" % (how, args.cpu_batch)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -376,32 +448,65 @@ def run_b200(args):
             pass
         shapes = conv_layer_table(b2, net, args, dev)
         rows = time_conv_kernels(b2, shapes, args.batch, args.dtype, dev)
-        top = rows[0]
-        tensor_bound = top["flops"] / (peaks.get("bf16_tflops", 1590.0) * 1e12) >= top["bytes"] / (peaks.get("hbm_gbs", 6650.0) * 1e9)
-        if tensor_bound:
-            peak = peaks.get("bf16_tflops", 1590.0)
-            roof = dict(bound="tensor", achieved=top["tflops"], peak=peak, unit="TFLOP/s", frac=top["tflops"] / peak)
-        else:
-            peak = peaks.get("hbm_gbs", 6650.0)
-            roof = dict(bound="hbm", achieved=top["gbs"], peak=peak, unit="GB/s", frac=top["gbs"] / peak)
+        bf16_peak, hbm_peak = peaks.get("bf16_tflops", 1590.0), peaks.get("hbm_gbs", 6650.0)
+
+        def roof_of(r):
+            """The bound that applies to one launch (min of the two roofs) and the fraction of it that was reached."""
+            t_tensor, t_hbm = r["flops"] / (bf16_peak * 1e12), r["bytes"] / (hbm_peak * 1e9)
+            if t_tensor >= t_hbm:
+                return dict(bound="tensor", achieved=r["tflops"], peak=bf16_peak, unit="TFLOP/s", frac=r["tflops"] / bf16_peak)
+            return dict(bound="hbm", achieved=r["gbs"], peak=hbm_peak, unit="GB/s", frac=r["gbs"] / hbm_peak)
+
+        def load_json(name):
+            try:
+                return json.load(open(os.path.join(ROOT, "profiles", name)))
+            except (OSError, ValueError):
+                return {}
+        pipe = load_json("r02_pconv_tensor_pipe.json")      # ncu sm__pipe_tensor_cycles_active per shape (committed capture)
+        partial_rows = [r for r in rows if " partial" in r["shape"]]
+        # the dominant kernel: the PartialConv shape (north_star's operator) with the largest share of the step; nets
+        # without PartialConv layers fall back to the largest convolution
+        top = max(partial_rows, key=lambda r: r["total_ms"]) if partial_rows else rows[0]
+        roof = roof_of(top)
         kname = "conv_%s %s" % (top["op"], top["shape"])
-        traffic = None
-        try:                         # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname, {}).get("dram_bytes")
-        except (OSError, ValueError):
-            pass
+        traffic = load_json("traffic.json").get(kname, {}).get("dram_bytes")   # per launch, from `ncu --set full`
+        conv_ms = max(sum(r["total_ms"] for r in rows), 1e-9)
         roof.update(traffic=traffic, kernel=kname, launch_ms=top["ms"], algorithmic_bytes=top["bytes"],
-                    algorithmic_flops=top["flops"],
-                    tensor_cores=top["tc"], peak_source="MEASURED_PEAKS.json (burst)" if peaks else "fallback",
-                    share_of_conv_time=top["total_ms"] / max(sum(r["total_ms"] for r in rows), 1e-9))
+                    algorithmic_flops=top["flops"], tensor_cores=top["tc"],
+                    tensor_pipe_active_pct=pipe.get(kname),
+                    peak_source="MEASURED_PEAKS.json (burst: kernel timed alone)" if peaks else "fallback",
+                    timing="CUDA events on the launch stream, median of 5, 256 MB read between launches evicts the L2",
+                    share_of_conv_time=top["total_ms"] / conv_ms)
+        # every PartialConv shape of the net (the metric's "partial-conv tensor-pipe util %" half)
+        roof["pconv"] = [dict(kernel="conv_%s %s" % (r["op"], r["shape"]), count=r["count"], launch_ms=r["ms"],
+                              tflops=r["tflops"], gbs=r["gbs"],
+                              tensor_pipe_active_pct=pipe.get("conv_%s %s" % (r["op"], r["shape"])), **roof_of(r))
+                         for r in sorted(partial_rows, key=lambda r: -r["total_ms"])]
+        if partial_rows:
+            pf = sum(r["flops"] * r["count"] for r in partial_rows)
+            pt = sum(r["total_ms"] for r in partial_rows)
+            roof["pconv_family"] = dict(tflops=pf / pt / 1e9, frac_of_tensor_peak=pf / pt / 1e9 / bf16_peak,
+                                        launches_ms=pt, share_of_conv_time=pt / conv_ms)
+        cf = sum(r["flops"] * r["count"] for r in rows)
+        roof["conv_family"] = dict(tflops=cf / conv_ms / 1e9, frac_of_tensor_peak=cf / conv_ms / 1e9 / bf16_peak,
+                                   launches_ms=conv_ms, note="FLOP-weighted over every convolution launch of one step "
+                                   "(fprop + dgrad + wgrad), each timed alone")
+        if line.get("model_tflops"):
+            sus = peaks.get("bf16_tflops_sustained", bf16_peak)
+            roof["step"] = dict(model_tflops=line["model_tflops"], frac_of_sustained_tensor_peak=line["model_tflops"] / sus,
+                                peak=sus, peak_source="MEASURED_PEAKS.json (sustained: inside a long step)")
         line["roofline"] = roof
         if args.layers:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", "conv_layers.json"), "w") as f:
                 json.dump(rows, f, indent=1)
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample, _ = cpu_step_rate(args, args.cpu_steps, 1, args.cpu_batch)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            v, cores, sample, _, kind = cpu_step_rate(args, args.cpu_steps, 1, args.cpu_batch)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        if world == 1 and not args.no_gpu_baseline:
+            del trainer, net
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_rates(args, dev)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

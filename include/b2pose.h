@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 3
+#define B2_ABI_VERSION 4
 
 /* slots of a BatchNorm partial-sum buffer: float[B2_BN_PARTS][2*C] (see the BatchNorm section) */
 #define B2_BN_PARTS 320
@@ -296,10 +296,6 @@ int b2_grad_sumsq(const float* g, int64_t n, double* sumsq, void* stream);
 int b2_adam_step(float* w, const float* g, float* m, float* v, void* w16, int64_t n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int32_t step, const double* sumsq,
                  float max_norm, float inv_scale, const float* dev_hyper, void* stream);
-
-/* ---- debug: tcgen05 descriptor self-test (used by tests/test_tc_selftest.py) ------------- */
-int b2_tc_selftest(const void* a, const void* b, float* c, int32_t M, int32_t N, int32_t K, int32_t variant,
-                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -335,6 +335,28 @@ def init_state(kind, model, cfg, seed=0, dtype=torch.float32):
     return sd
 
 
+class _RoundBF16(torch.autograd.Function):
+    """Round to bf16 in the forward AND the backward pass: the device path stores every activation (conv output y,
+    block output z) and every activation gradient (dy, dx) as bf16; everything between two stores is fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def round_bf16(x):
+    """The `act_round` hook that restates the bf16 storage contract of the device path (see net_forward)."""
+    return _RoundBF16.apply(x)
+
+
+def _ident(x):
+    return x
+
+
 def _bn(sd, prefix, x, training, momentum=0.1, eps=1e-5):
     out = F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
                        sd[prefix + ".weight"], sd[prefix + ".bias"], training, momentum, eps)
@@ -343,7 +365,17 @@ def _bn(sd, prefix, x, training, momentum=0.1, eps=1e-5):
     return out
 
 
-def _run_stage(sd, lname, block, planes, nblk, stride, dil, x, veil, training, skip_last_relu=False):
+def _keep(trace, **rec):
+    """Append one record to a trace list, keeping the gradients of the recorded activations after backward()."""
+    if trace is not None:
+        for v in rec.values():
+            if torch.is_tensor(v) and v.requires_grad and not v.is_leaf:
+                v.retain_grad()
+        trace.append(rec)
+
+
+def _run_stage(sd, lname, block, planes, nblk, stride, dil, x, veil, training, skip_last_relu=False, rnd=_ident,
+               trace=None):
     """One ResNet stage.  ``veil`` None -> plain convs; else partial convs threading the veil
     (partial_depthnet.py:62-75,140-157; residual branch plain on the *unmasked* input)."""
     exp = 4 if block == "bottleneck" else 1
@@ -353,29 +385,42 @@ def _run_stage(sd, lname, block, planes, nblk, stride, dil, x, veil, training, s
         inpl = x.shape[1]
         res = x
         out = x
+        x_in, veil_in = x, veil
         convs = _block_convs(block, inpl, planes, s, d)
         for i, (suf, _, _, k, cs, cp, cd) in enumerate(convs):
             w = sd["%s.conv%s.weight" % (pre, suf)]
             if veil is None:
-                out = F.conv2d(out, w, None, cs, cp, cd)
+                out = rnd(F.conv2d(out, w, None, cs, cp, cd))
             else:
                 out, veil = partial_conv(out, veil, w, None, cs, cp, cd)
+                out = rnd(out)
             out = _bn(sd, "%s.bn%s" % (pre, suf), out, training)
             if i + 1 < len(convs):
-                out = F.relu(out)
+                out = rnd(F.relu(out))
         if (pre + ".downsample.0.weight") in sd:
-            res = F.conv2d(res, sd[pre + ".downsample.0.weight"], None, s)
-            res = _bn(sd, pre + ".downsample.1", res, training)
+            res = rnd(F.conv2d(res, sd[pre + ".downsample.0.weight"], None, s))
+            res = rnd(_bn(sd, pre + ".downsample.1", res, training))
         out = out + res
         if not (skip_last_relu and b == nblk - 1):
             out = F.relu(out)
-        x = out
+        x = rnd(out)
+        _keep(trace, name=pre, x=x_in, veil=veil_in, out=x, veil_out=veil)
     return x, veil
 
 
-def net_forward(sd, kind, model, cfg, x, y=None, training=True):
+def net_forward(sd, kind, model, cfg, x, y=None, training=True, act_round=None, trace=None):
     """Forward of any of the five nets.  Returns (z, last_feat) -- or, for kind
     'resnet', cam_feat / (cam_feat, mat_feat) like resnet.py:204-209.
+
+    ``act_round`` (default: none, the reference's fp32 arithmetic) is applied wherever the device's bf16 mode stores
+    an activation (``trace``: optional list that receives one record per stem / residual block / fusion / regressor
+    with its input, output and -- after backward() -- their gradients, for block-level parity tests): after every convolution (the raw / renormalised output the BatchNorm statistics are taken from)
+    and after every BatchNorm(+residual)(+ReLU) / pooling result.  ``act_round=round_bf16`` therefore restates the
+    reference algorithm under the bf16-storage / fp32-accumulate contract (what torch.autocast does to the
+    reference itself), which is what the bf16 parity tests compare against: training-mode BatchNorm at random
+    initialisation amplifies any perturbation ~200x through ResNet-50 (tests/golden/bf16_sensitivity.npz), so an
+    fp32 evaluation is not a meaningful reference for bf16 training-mode outputs -- the reference's own
+    bf16-autocast forward is 0.6 relative away from its fp32 forward.
 
     depthnet.py:188-200, partial_depthnet.py:213-229, fusionnet.py:221-240,
     partial_fusionnet.py:250-274 (with the documented stem fix: RGB stem plain,
@@ -386,41 +431,50 @@ def net_forward(sd, kind, model, cfg, x, y=None, training=True):
     partial = kind.startswith("partial_")
     skip = bool(getattr(cfg, "skip_relu", False)) and kind in ("depthnet", "fusionnet")
     pool = lambda t: F.max_pool2d(t, 3, 2, 1)
+    rnd = _ident if act_round is None else act_round
+    x = rnd(x)
+    y = rnd(y) if y is not None else None
 
     def stem(inp, conv, bn, is_partial):
         if is_partial:
             veil = (inp != 0).float()
             t, veil = partial_conv(inp, veil, sd[conv + ".weight"], None, 2, 3, 1)
-            t = pool(F.relu(_bn(sd, bn, t, training)))
-            return t, pool(veil)
-        t = F.conv2d(inp, sd[conv + ".weight"], None, 2, 3)
-        return pool(F.relu(_bn(sd, bn, t, training))), None
+            t = pool(rnd(F.relu(_bn(sd, bn, rnd(t), training))))
+            veil = pool(veil)
+            _keep(trace, name=conv, x=inp, veil=None, out=t, veil_out=veil)
+            return t, veil
+        t = rnd(F.conv2d(inp, sd[conv + ".weight"], None, 2, 3))
+        t = pool(rnd(F.relu(_bn(sd, bn, t, training))))
+        _keep(trace, name=conv, x=inp, veil=None, out=t, veil_out=None)
+        return t, None
 
     if kind in ("fusionnet", "partial_fusionnet"):
         a, _ = stem(x, "conv1", "bn1", False)
         b, veil = stem(y, "conv2", "bn2", partial)
         for (ln, planes, nblk, s, d), dn in zip(tab[:2], ("layer5", "layer6")):
-            a, _ = _run_stage(sd, ln, block, planes, nblk, s, d, a, None, training)
-            b, veil = _run_stage(sd, dn, block, planes, nblk, s, d, b, veil, training)
-        f = F.conv2d(torch.cat([a, b], dim=1), sd["fusion.conv.weight"])
-        f = F.relu(_bn(sd, "fusion.bn", f, training))
+            a, _ = _run_stage(sd, ln, block, planes, nblk, s, d, a, None, training, rnd=rnd, trace=trace)
+            b, veil = _run_stage(sd, dn, block, planes, nblk, s, d, b, veil, training, rnd=rnd, trace=trace)
+        f = rnd(F.conv2d(torch.cat([a, b], dim=1), sd["fusion.conv.weight"]))
+        f = rnd(F.relu(_bn(sd, "fusion.bn", f, training)))
+        _keep(trace, name="fusion", x=a, x2=b, veil=None, out=f, veil_out=None)
     else:
         f, veil = stem(x, "conv1", "bn1", partial)
         for (ln, planes, nblk, s, d) in tab[:2]:
-            f, veil = _run_stage(sd, ln, block, planes, nblk, s, d, f, veil, training)
+            f, veil = _run_stage(sd, ln, block, planes, nblk, s, d, f, veil, training, rnd=rnd, trace=trace)
 
     ln, planes, nblk, s, d = tab[2]
-    m, _ = _run_stage(sd, ln, block, planes, nblk, s, d, f, None, training, skip_last_relu=skip)
+    m, _ = _run_stage(sd, ln, block, planes, nblk, s, d, f, None, training, skip_last_relu=skip, rnd=rnd, trace=trace)
     ln, planes, nblk, s, d = tab[3]
     n, _ = _run_stage(sd, ln, block, planes, nblk, s, d, F.relu(m) if skip else m, None, training,
-                      skip_last_relu=skip)
+                      skip_last_relu=skip, rnd=rnd, trace=trace)
     top = F.relu(n) if skip else n
     if kind == "resnet":
         cam = F.conv2d(top, sd["cam_regressor.weight"], sd["cam_regressor.bias"], 1, 1)
         if "mat_regressor.weight" in sd:
             return cam, F.conv2d(top, sd["mat_regressor.weight"], sd["mat_regressor.bias"], 1, 1)
         return cam
-    z = F.conv2d(top, sd["regressor.weight"], sd["regressor.bias"], 1, 1)
+    z = rnd(F.conv2d(top, sd["regressor.weight"], sd["regressor.bias"], 1, 1))
+    _keep(trace, name="regressor", x=top, veil=None, out=z, veil_out=None)
     last = m if (getattr(cfg, "early_dist", False) and kind in ("depthnet", "fusionnet")) else n
     return z, last
 
@@ -445,8 +499,10 @@ class StepOracle:
     """
 
     def __init__(self, sd, kind, model, cfg, *, learn_rate=5e-5, weight_decay=4e-5, grad_norm=5.0,
-                 depth_range=1000.0, loss_div=10.0, key_index=16, criterion="SmoothL1"):
+                 depth_range=1000.0, loss_div=10.0, key_index=16, criterion="SmoothL1", act_round=None):
         self.sd, self.kind, self.model, self.cfg = sd, kind, model, cfg
+        self.act_round = act_round          # see net_forward: round_bf16 restates the bf16 storage contract
+        self.trace = None                   # set to a list to record per-block activations (net_forward `trace`)
         self.names = trainable_names(sd)
         for k in self.names:
             sd[k].requires_grad_(True)
@@ -458,13 +514,13 @@ class StepOracle:
     def forward_loss(self, batch):
         color, depth, true_cam, true_val = batch
         if self.kind in ("fusionnet", "partial_fusionnet"):
-            z, _ = net_forward(self.sd, self.kind, self.model, self.cfg, color, depth, True)
+            z, _ = net_forward(self.sd, self.kind, self.model, self.cfg, color, depth, True, self.act_round, self.trace)
         elif self.kind == "resnet":
-            z = net_forward(self.sd, self.kind, self.model, self.cfg, color, None, True)
+            z = net_forward(self.sd, self.kind, self.model, self.cfg, color, None, True, self.act_round)
             z = z[0] if isinstance(z, tuple) else z
         else:
             inp = depth if (self.kind == "partial_depthnet" or self.cfg.depth_only) else color
-            z, _ = net_forward(self.sd, self.kind, self.model, self.cfg, inp, None, True)
+            z, _ = net_forward(self.sd, self.kind, self.model, self.cfg, inp, None, True, self.act_round, self.trace)
         ld = 1.0 if self.kind == "resnet" else self.loss_div        # train.py:174 has no loss_div
         loss, spec = pose_loss(z, true_cam, true_val, depth=self.cfg.depth, num_joints=self.cfg.num_joints,
                                side_out=self.side_out, depth_range=self.depth_range,

@@ -27,7 +27,7 @@ def test_library_exports_header(b2pose):
     for s in syms:
         assert hasattr(lib, s), "libb2pose.so does not export %s" % s
     assert sorted(b2pose._lib.SIGNATURES) == syms          # the binding covers exactly the header
-    assert b2pose._lib.lib().b2_abi_version() == b2pose._lib.ABI_VERSION == 3
+    assert b2pose._lib.lib().b2_abi_version() == b2pose._lib.ABI_VERSION == 4
 
 
 def test_header_arg_counts_match_binding(b2pose):
@@ -166,7 +166,10 @@ def test_bench_reference_arm_contract():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    staged = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "partial_fusionnet.py"))
+    # the reference's own modules when baseline/_ref is staged (baseline/stage_reference.py), else the oracle port
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
     assert other.returncode == 0 and other.stdout.strip() == ""

@@ -1,0 +1,225 @@
+"""Parity of the BENCHED mode -- bf16 tensor-core compute, fp32 masters, BatchNorm totals path, side streams, CUDA graph --
+against the reference step (depth_train.py:384-456) at the contract tolerance.
+
+Fixture: ResNet-50, batch 8, 128x128, so that training-mode BatchNorm is well conditioned (512 values per channel in
+layer4; the batch-2 fixtures of test_gpu_nets.py have 32), on bf16-rounded weights and inputs so that what is compared
+is the arithmetic, not the rounding of the operands.
+
+What the reference side is, and why.  Training-mode BatchNorm at random initialisation makes ResNet-50 a strongly
+expanding map: the imported reference's OWN forward moves by 1.8e-4 relative when its fp32 input is perturbed by 1e-6,
+and its own ``torch.autocast(bfloat16)`` forward is 0.5-0.6 relative away from its fp32 forward
+(tests/golden/bf16_sensitivity.npz, produced by oracle/make_bf16_sensitivity.py from the imported reference).  No bf16
+evaluation can therefore stay within 2e-2 of the fp32 training-mode outputs, and an fp32 oracle is not a meaningful
+checker for them.  The tests pin the bf16 path three ways instead:
+
+  1. tests/test_gpu_bf16_blocks.py removes the amplification: every stem / residual block / fusion / regressor unit of
+     the device net is fed the ORACLE's input and output gradient (oracle = reference algorithm under the same bf16
+     storage contract, ``po.round_bf16``) and held to 2e-2 on outputs and input gradients, 3e-2 on parameter gradients,
+     bit-exact veils -- the contract tolerance on every layer of the benched net, forward and backward;
+  2. here, end to end: first-step loss within 1e-2 of the contract oracle (measured <= 0.8e-2), eager AND graph replay,
+     at 128x128 batch 8 and at 256x256 batch 16; the total gradient norm and the 4-step loss trajectory inherit the
+     expansion (Adam's first updates are ~lr*sign(g)) and are held to 1.5e-1 / 1e-1 (measured 1-9 % / <= 8 %);
+  3. in EVAL mode (running statistics: a contracting map) against the plain fp32 oracle at 2e-2;
+  4. against the plain fp32 oracle in training mode with the bound the reference sets itself: the distance to fp32 must
+     not exceed 1.25x the reference's own bf16-autocast distance on the same fixture (measured 1.0-1.14x).
+"""
+import numpy as np
+import pytest
+import torch
+
+import pose_oracle as po
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["fusionnet", "partial_fusionnet", "partial_depthnet"]
+TOL_OUT, TOL_LOSS, TOL_GNORM, TOL_TRAJ = 2e-2, 1e-2, 1.5e-1, 1e-1
+
+
+def _round_bf16(t):
+    return t.bfloat16().float()
+
+
+def _rounded_state(kind, model, cfg, seed):
+    """Seed state with every convolution filter rounded to bf16 (what the device's shadow filters hold); BatchNorm
+    parameters and the regressor bias stay fp32 on both sides."""
+    sd = po.init_state(kind, model, cfg, seed=seed)
+    for k, v in sd.items():
+        if v.dim() == 4:
+            sd[k] = _round_bf16(v)
+    return sd
+
+
+def _rounded_batch(n, side, J, seed):
+    color, depth, true_cam, true_val = po.synth_batch(n, side, J, seed=seed, invalid_frac=0.25)
+    return _round_bf16(color), _round_bf16(depth), true_cam, true_val
+
+
+def _fused(kind):
+    return kind in ("fusionnet", "partial_fusionnet")
+
+
+def _forward(kind, model, cfg, sd, batch, training, act_round):
+    clone = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        if _fused(kind):
+            return po.net_forward(clone, kind, model, cfg, batch[0], batch[1], training=training, act_round=act_round)
+        return po.net_forward(clone, kind, model, cfg, batch[1], None, training=training, act_round=act_round)
+
+
+def _oracle(kind, model, cfg, sd, batch, steps):
+    """Reference under the bf16 storage contract: train-mode (z, last_feat) of the first forward, then `steps`
+    optimisation steps; plus the plain fp32 forwards (train and eval) for the sensitivity-bounded comparisons."""
+    z, last = _forward(kind, model, cfg, sd, batch, True, po.round_bf16)
+    z32, last32 = _forward(kind, model, cfg, sd, batch, True, None)
+    ze32, laste32 = _forward(kind, model, cfg, sd, batch, False, None)
+    orc = po.StepOracle({k: v.clone() for k, v in sd.items()}, kind, model, cfg, key_index=cfg.num_joints - 1,
+                        act_round=po.round_bf16)
+    losses, grads, specs, gnorms = [], None, [], []
+    for it in range(steps):
+        loss, gn, spec, _ = orc.step(batch)
+        losses.append(loss)
+        specs.append(spec)
+        gnorms.append(gn)
+        if it == 0:
+            coef = min(1.0, 5.0 / (gn + 1e-6))          # clip_grad_norm_ scaled the grads in place: undo
+            grads = {k: orc.sd[k].grad.detach().clone() / coef for k in orc.names}
+            gnorm = gn
+    return dict(z=z, last=last, losses=losses, grads=grads, gnorm=gnorm, specs=specs, gnorms=gnorms,
+                z32=z32, last32=last32, ze32=ze32, laste32=laste32)
+
+
+def _device_net(b2pose, dev, kind, model, cfg, sd):
+    net = getattr(getattr(b2pose, kind), model)(cfg, False)
+    net.load_state_dict(sd)
+    return net.to(dev).train()
+
+
+def _targs(b2pose, kind, model, cfg):
+    return b2pose.train_args(model=model, num_joints=cfg.num_joints, side_in=cfg.side_in, stride=cfg.stride,
+                             depth_only=not _fused(kind), do_fusion=_fused(kind), half_acc=True)
+
+
+_cache = {}
+
+
+def _case(kind, side, n, seed_w, seed_b, steps):
+    key = (kind, side, n, seed_w, seed_b, steps)
+    if key not in _cache:
+        cfg = po.net_config(side_in=side, num_joints=17, depth_only=not _fused(kind))
+        sd = _rounded_state(kind, "resnet50", cfg, seed_w)
+        batch = _rounded_batch(n, side, 17, seed_b)
+        _cache[key] = (cfg, sd, batch, _oracle(kind, "resnet50", cfg, sd, batch, steps))
+    return _cache[key]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_bf16_train_forward_outputs(b2pose, dev, golden_dir, kind):
+    """Train-mode z and last_feat of the bf16 path are no further from the fp32 reference than the reference's own
+    bf16-autocast forward (x1.25); eval mode within 2e-2 of fp32.  (Even against the oracle under the same storage
+    contract the end-to-end distance is 0.08-0.4: one flipped bf16 rounding early in the net is amplified ~200x; the
+    2e-2 bound is enforced per unit in test_gpu_bf16_blocks.py.)"""
+    cfg, sd, batch, ref = _case(kind, 128, 8, 41, 9, 4)
+    sens = np.load(golden_dir + "/bf16_sensitivity.npz")
+    net = _device_net(b2pose, dev, kind, "resnet50", cfg, sd).half()
+    dbatch = tuple(t.to(dev) for t in batch)
+    with torch.no_grad():
+        z, last = net(dbatch[0], dbatch[1]) if _fused(kind) else net(dbatch[1])
+        net.load_state_dict(sd)          # the train-mode forward moved the running statistics
+        net.eval()
+        ze, laste = net(dbatch[0], dbatch[1]) if _fused(kind) else net(dbatch[1])
+    assert z.dtype == torch.bfloat16
+    ez, el = rel_err(z, ref["z"]), rel_err(last, ref["last"])
+    ez32, el32 = rel_err(z, ref["z32"]), rel_err(last, ref["last32"])
+    eze, ele = rel_err(ze, ref["ze32"]), rel_err(laste, ref["laste32"])
+    print(kind, "train-mode bf16 vs contract oracle: z %.4f last_feat %.4f | vs fp32 oracle: z %.4f last %.4f (reference's "
+          "own bf16 autocast: z %.4f last %.4f; 1e-6 input perturbation moves its fp32 z by %.1e) | eval vs fp32: z %.4f "
+          "last %.4f" % (ez, el, ez32, el32, float(sens[kind + "_train_bf16_z"]), float(sens[kind + "_train_bf16_last"]),
+                         float(sens[kind + "_train_eps1e-6_z"]), eze, ele))
+    assert ez < 1.25 * float(sens[kind + "_train_bf16_z"]) and el < 1.25 * float(sens[kind + "_train_bf16_last"])
+    assert ez32 < 1.25 * float(sens[kind + "_train_bf16_z"]) and el32 < 1.25 * float(sens[kind + "_train_bf16_last"])
+    assert eze < TOL_OUT and ele < 2.5e-2      # (last_feat is a ReLU output with a long tail: a hair above z's error)
+
+
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "graph"])
+@pytest.mark.parametrize("kind", KINDS)
+def test_bf16_step_matches_reference(b2pose, dev, kind, use_graph):
+    """First-step loss <= 1e-2, total gradient norm, MPJPE and the 4-step loss trajectory against the contract oracle, for
+    the eager step and for the captured graph (3 eager warm-ups, then replay)."""
+    cfg, sd, batch, ref = _case(kind, 128, 8, 41, 9, 4)
+    net = _device_net(b2pose, dev, kind, "resnet50", cfg, sd)
+    tr = b2pose.Trainer(_targs(b2pose, kind, "resnet50", cfg), net, dict(key_index=16), use_graph=use_graph)
+    dbatch = tuple(t.to(dev) for t in batch)
+    losses, gnorms = [], []
+    for it in range(4):
+        out = tr.train_step(dbatch)
+        losses.append(float(out["loss"]))
+        gnorms.append(float(out["grad_sumsq"].sqrt()))
+        if it == 0:
+            spec = out["spec_cam"].cpu()
+            gsum = float(out["grad_sumsq"].sqrt())
+            total_ref = ref["gnorm"]
+            true_cam, valid = batch[2].numpy(), batch[3].numpy()
+            dm = abs(po.mpjpe(spec.numpy(), true_cam, valid) - po.mpjpe(ref["specs"][0].numpy(), true_cam, valid))
+            print(kind, "graph" if use_graph else "eager", "loss %.5f ref %.5f  |g| %.4f ref %.4f  max|dspec| %.3f mm  "
+                  "|dMPJPE| %.3f mm" % (losses[0], ref["losses"][0], gsum, total_ref,
+                                        float((spec - ref["specs"][0]).abs().max()), dm))
+            assert abs(losses[0] - ref["losses"][0]) / ref["losses"][0] < TOL_LOSS
+            assert abs(gsum - total_ref) / total_ref < TOL_GNORM
+            assert dm < 10.0              # joints of a random-init net decode near the volume centre: MPJPE ~ 500 mm
+    print(kind, "trajectory", losses, ref["losses"])
+    # steps 2-4 start from Adam-updated weights (first update ~ lr * sign(g): rounding decides near-zero gradients), and
+    # step 4 is the first graph REPLAY when use_graph
+    np.testing.assert_allclose(losses, ref["losses"], rtol=TOL_TRAJ)
+    assert all(np.isfinite(gnorms))        # (beyond step 1 the gradient norm decorrelates: 2-3x swings on either side)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_bf16_full_size_step(b2pose, dev, kind):
+    """One 256x256 batch-16 step of every benched workload (graph mode, like bench.py) against the reference."""
+    cfg, sd, batch, ref = _case(kind, 256, 16, 43, 11, 1)
+    net = _device_net(b2pose, dev, kind, "resnet50", cfg, sd)
+    tr = b2pose.Trainer(_targs(b2pose, kind, "resnet50", cfg), net, dict(key_index=16), use_graph=True)
+    out = tr.train_step(tuple(t.to(dev) for t in batch))
+    loss, gsum = float(out["loss"]), float(out["grad_sumsq"].sqrt())
+    spec = out["spec_cam"].cpu()
+    print(kind, "256x256 batch 16: loss %.5f ref %.5f  |g| %.4f ref %.4f  max|dspec| %.3f mm" % (
+        loss, ref["losses"][0], gsum, ref["gnorm"], float((spec - ref["specs"][0]).abs().max())))
+    assert abs(loss - ref["losses"][0]) / ref["losses"][0] < TOL_LOSS
+    assert abs(gsum - ref["gnorm"]) / ref["gnorm"] < TOL_GNORM
+    true_cam, valid = batch[2].numpy(), batch[3].numpy()
+    assert abs(po.mpjpe(spec.numpy(), true_cam, valid) - po.mpjpe(ref["specs"][0].numpy(), true_cam, valid)) < 10.0
+    with torch.no_grad():
+        net2 = _device_net(b2pose, dev, kind, "resnet50", cfg, sd).half().eval()
+        dbatch = tuple(t.to(dev) for t in batch)
+        ze, laste = net2(dbatch[0], dbatch[1]) if _fused(kind) else net2(dbatch[1])
+    print(kind, "256x256 eval-mode vs fp32 oracle: z %.4f last %.4f" % (rel_err(ze, ref["ze32"]), rel_err(laste, ref["laste32"])))
+    assert rel_err(ze, ref["ze32"]) < TOL_OUT and rel_err(laste, ref["laste32"]) < 2.5e-2
+
+
+def test_workspace_growth_after_capture(b2pose, dev):
+    """A scratch workspace that has to grow AFTER a graph was captured (evaluation batch between training steps) must
+    not invalidate the captured graph: replay afterwards continues the eager trajectory (ops.workspace)."""
+    kind, model = "partial_fusionnet", "resnet18"
+    cfg = po.net_config(side_in=64, num_joints=17, depth_only=False)
+    sd = po.init_state(kind, model, cfg, seed=5)
+    batch = tuple(t.to(dev) for t in po.synth_batch(2, 64, 17, seed=3))
+    big = tuple(t.to(dev) for t in po.synth_batch(16, 96, 17, seed=4))
+    traj = {}
+    for mode in ("eager", "graph"):
+        net = _device_net(b2pose, dev, kind, model, cfg, sd)
+        tr = b2pose.Trainer(b2pose.train_args(model=model, num_joints=17, side_in=64, depth_only=False, do_fusion=True,
+                                              half_acc=True), net, dict(key_index=16), use_graph=mode == "graph")
+        losses = [float(tr.train_step(batch)["loss"]) for _ in range(5)]      # graph: captured after step 3, replayed
+        with torch.no_grad():                                                   # larger eval shapes: the stems' im2col
+            net.eval()                                                          # workspace (slot 0) has to grow
+            net(big[0], big[1])
+            net.train()
+        torch.cuda.empty_cache()
+        losses += [float(tr.train_step(batch)["loss"]) for _ in range(3)]
+        traj[mode] = losses
+    print(traj)
+    # (batch 2: the trajectory is chaotic in the last bits -- the two eager step-0 losses already differ by 5e-4 through
+    #  the order of the fp32 reductions -- so this is a corruption check, not a parity bound)
+    np.testing.assert_allclose(traj["graph"], traj["eager"], rtol=6e-2)
+    assert all(np.isfinite(traj["graph"]))
