@@ -31,6 +31,7 @@ _D = C.POINTER(ConvDesc)
 SIGNATURES = {
     "b2_abi_version": [],
     "b2_last_error": [],
+    "b2_set_sm_reserve": [_i],
     "b2_conv_uses_tensor_cores": [_D, _i],
     "b2_conv_workspace_bytes": [_D, _i],
     "b2_pconv_fprop": [_D, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p],
@@ -45,6 +46,7 @@ SIGNATURES = {
     "b2_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _p],
     "b2_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
     "b2_cast_f32_to_bf16": [_p, _p, _l, _p],
+    "b2_cast_bf16_to_f32": [_p, _p, _l, _p],
     "b2_bn_stats": [_p, _l, _i, _i, _p, _p],
     "b2_bn_finalize": [_p, _l, _i, _p, _p, _f, _f, _i, _p, _p, _p],
     "b2_bn_apply": [_p, _p, _p, _p, _p, _p, _p, _i, _p, _l, _i, _i, _p],

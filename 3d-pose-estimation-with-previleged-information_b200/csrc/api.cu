@@ -14,7 +14,14 @@ void b2_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int g_b2_sm_reserve = 0;
+
 extern "C" int b2_abi_version(void) { return B2_ABI_VERSION; }
+extern "C" int b2_set_sm_reserve(int32_t sms) {
+  B2_REQUIRE(sms >= 0 && sms < 128, B2_E_BADARG, "set_sm_reserve: %d SMs", sms);
+  g_b2_sm_reserve = sms;
+  return B2_OK;
+}
 extern "C" const char* b2_last_error(void) { return g_err; }
 
 static int check_desc(const B2ConvDesc* d) {

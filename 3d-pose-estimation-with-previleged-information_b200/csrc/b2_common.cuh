@@ -162,6 +162,10 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// SMs the grids of this library may fill: the device's count minus the SMs the caller reserved for kernels running
+// beside ours (b2_set_sm_reserve: the NCCL kernels of an overlapped gradient all-reduce -- a persistent one-CTA-per-SM
+// grid whose last CTAs have to wait for an SM that a collective holds takes twice as long).
+extern int g_b2_sm_reserve;
 static inline int b2_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -170,7 +174,8 @@ static inline int b2_num_sms() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  return sms;
+  const int n = sms - g_b2_sm_reserve;
+  return n < 1 ? 1 : n;
 }
 
 // ---- internal entry points (defined in the .cu files, dispatched from api.cu) ----

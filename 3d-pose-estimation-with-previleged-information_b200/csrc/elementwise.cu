@@ -100,6 +100,13 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[n4 * 4 + threadIdx.x] = __float2bfloat16_rn(src[n4 * 4 + threadIdx.x]);
 }
 
+__global__ void cast_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    store4(dst + i * 4, load4(src + i * 4));
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[n4 * 4 + threadIdx.x] = __bfloat162float(src[n4 * 4 + threadIdx.x]);
+}
+
 // NCHW fp32 -> NHWC T through a shared-memory transpose of [C-chunk x 32 pixels]
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int C, long long HW) {
@@ -378,6 +385,15 @@ extern "C" int b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void*
   B2_REQUIRE((((uintptr_t)src) & 15) == 0 && (((uintptr_t)dst) & 7) == 0, B2_E_BADARG, "cast: unaligned pointer");
   cast_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
   B2_LAUNCH_CHECK("cast_f32_to_bf16");
+  return B2_OK;
+}
+
+extern "C" int b2_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  B2_REQUIRE(src && dst && n >= 0, B2_E_BADARG, "cast: bad argument");
+  if (n == 0) return B2_OK;
+  B2_REQUIRE((((uintptr_t)dst) & 15) == 0 && (((uintptr_t)src) & 7) == 0, B2_E_BADARG, "cast: unaligned pointer");
+  cast_f32_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+  B2_LAUNCH_CHECK("cast_bf16_to_f32");
   return B2_OK;
 }
 

@@ -273,6 +273,10 @@ class ResNet(nn.Module):
             f, veil = self._stem(x, self.conv1, self.bn1)
             f, veil = self._run(self.layer1, f, veil)
             f, veil = self._run(self.layer2, f, veil)
+        # f = input of layer3: the boundary between the shallow (stems, layer1/2/5/6, fusion) and the deep part; a
+        # data-parallel Trainer runs the backward pass in two stages around it so that the all-reduce of the deep
+        # gradients (~90 % of the parameters) overlaps the shallow backward (trainer.Trainer._fwd_bwd_deep)
+        self._boundary = f if getattr(self, "_mark_boundary", False) else None
         m, _ = self._run(self.layer3, f, None)
         n, _ = self._run(self.layer4, torch.relu(m) if self.skip_relu else m, None)
         top = torch.relu(n) if self.skip_relu else n

@@ -303,6 +303,16 @@ def _prepare_dgrad_filter(desc, wk):
     return wt
 
 
+def wgrad_overlap_join(device):
+    """Mid-step join (two-stage backward): the main stream waits for the side-stream wgrads issued so far; the
+    overlap stays active for the second stage."""
+    o = _overlaps.get(device.index)
+    if o is None or not o.active:
+        return
+    o.main.wait_stream(o.stream)
+    o.keep = []
+
+
 def wgrad_overlap_end(device):
     """Join: the main stream waits for every side-stream wgrad; the kept tensors are released."""
     o = _overlaps.get(device.index)

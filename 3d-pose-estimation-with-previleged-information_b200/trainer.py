@@ -118,7 +118,7 @@ class _FlatState:
 
 
 class Trainer:
-    def __init__(self, args, model, data_info, use_graph=True, process_group=None, bucket_mb=25.0):
+    def __init__(self, args, model, data_info, use_graph=True, process_group=None, bucket_mb=128.0, overlap=None):
         self.model = model
         self.data_info = data_info
         self.key_index = data_info["key_index"] if isinstance(data_info, dict) else data_info.key_index
@@ -186,13 +186,32 @@ class Trainer:
         self._extras = {}
         self.pg = process_group
         self.world = 1
+        self.overlap = False
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             import torch.distributed as dist
             self.pg = process_group if process_group is not None else dist.group.WORLD
             self.world = dist.get_world_size(self.pg)
-            from .parallel import broadcast_flat, GradBuckets
+            from .parallel import broadcast_flat, GradBuckets, COMM_SMS
             broadcast_flat(self.flat, self.pg)
-            self.buckets = GradBuckets(self.flat, self.pg, bucket_mb)
+            # two-stage backward: layer3 / layer4 / regressor gradients (~90 % of the bytes) are complete when the
+            # backward pass reaches the input of layer3 and are all-reduced while the shallow half still computes
+            # (measured at 2 GPUs, profiles/r02_ddp_overlap.md: the overlapped exchange LOSES to one exposed all-reduce
+            #  -- 15.83-15.99 ms against 15.61 ms per step -- because the NCCL kernels take SMs away from the persistent
+            #  one-CTA-per-SM convolution grids; it stays available behind B2POSE_DDP_OVERLAP=1)
+            env = __import__("os").environ
+            self.overlap = overlap if overlap is not None else env.get("B2POSE_DDP_OVERLAP", "0") != "0"
+            # bf16 compute: exchange the gradients as bf16 too (they come out of bf16 activations); fp32 mode keeps fp32
+            compress = self.half_acc and env.get("B2POSE_DDP_BF16", "1") != "0"
+            deep = [(o, o + (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN)
+                    for name, p, o in zip(self.list_names, self.flat.params, self.flat.offsets)
+                    if name.startswith(("layer3.", "layer4.", "regressor.", "cam_regressor.", "mat_regressor."))]
+            # deep parameters that autograd (not a kernel sink) accumulates: the regressors' plain convolutions
+            self.deep_params = [p for name, p in zip(self.list_names, self.flat.params)
+                                if name.startswith(("regressor.", "cam_regressor.", "mat_regressor."))]
+            bucket_mb = float(env.get("B2POSE_BUCKET_MB", bucket_mb))
+            self.buckets = GradBuckets(self.flat, self.pg, bucket_mb, deep=deep if self.overlap else None,
+                                       compress=compress)
+            self.comm_sms = COMM_SMS
             for m in model.buffers():
                 dist.broadcast(m, 0, group=self.pg)
 
@@ -308,6 +327,48 @@ class Trainer:
             ops.bn_arena_end(self.device)
         return loss.detach(), spec
 
+    # ---- data parallel: backward in two stages around the input of layer3 (see nets.ResNet.forward) ----
+    def _two_stage(self, semi):
+        return self.overlap and self.world > 1 and semi is None and self.teacher is None
+
+    def _fwd_bwd_deep(self, batch):
+        """Stage 1: zero-grad, forward, head, loss, backward down to the input of layer3.  On return every gradient of
+        layer3 / layer4 / the regressor is in the flat buffer and the weight-gradient stream has been joined."""
+        self.flat.g.zero_()
+        ops.bn_arena_begin(self.device)
+        ops.wgrad_overlap_begin(self.device)
+        self.model._mark_boundary = True
+        try:
+            loss, spec = self._forward_loss(*batch)
+            f = self.model._boundary
+            ops.wgrad_overlap_sync(self.device)
+            # (parameters whose kernels do not write into the flat buffer themselves -- the regressor's plain ConvFn --
+            #  are accumulated by autograd: name them, torch.autograd.backward(inputs=...) skips everything else)
+            # retain_graph: without it the engine frees the saved tensors of the whole graph, including the shallow
+            # nodes it did not run; the second stage releases everything
+            torch.autograd.backward([loss], inputs=[f] + self.deep_params, retain_graph=True)
+            ops.wgrad_overlap_join(self.device)
+        except BaseException:
+            ops.wgrad_overlap_end(self.device)
+            ops.bn_arena_end(self.device)
+            raise
+        finally:
+            self.model._mark_boundary = False
+            self.model._boundary = None
+        self._stage2 = (f, f.grad)
+        f.grad = None
+        return loss.detach(), spec
+
+    def _bwd_shallow(self):
+        """Stage 2: the rest of the backward pass (fusion, layer1/2/5/6, stems)."""
+        f, df = self._stage2
+        self._stage2 = None
+        try:
+            torch.autograd.backward([f], [df])
+        finally:
+            ops.wgrad_overlap_end(self.device)
+            ops.bn_arena_end(self.device)
+
     def _update(self):
         f = self.flat
         self.sumsq.zero_()
@@ -406,12 +467,10 @@ class Trainer:
             key = (key, key2)
         dist_on = self.world > 1
         n0 = L.launches
+        two = self._two_stage(st_semi)
         if not self.use_graph:
-            loss, spec = self._fwd_bwd(st, st_semi)
+            loss, spec = self._eager_step(st, st_semi, two)
             extras = self._extras
-            if dist_on:
-                self.buckets.allreduce()
-            self._update()
             self.launches_per_step = L.launches - n0
         else:
             key = (key, self._mode_key())
@@ -419,17 +478,18 @@ class Trainer:
             if entry is None:
                 entry = self._capture(key, st)
             if entry["stage"] < 3:               # eager warm-up iterations before capture
-                loss, spec = self._fwd_bwd(st, st_semi)
+                loss, spec = self._eager_step(st, st_semi, two)
                 extras = self._extras
-                if dist_on:
-                    self.buckets.allreduce()
-                self._update()
                 entry["stage"] += 1
                 if entry["stage"] == 3:
-                    self._do_capture(entry, st, st_semi)
+                    self._do_capture(entry, st, st_semi, two)
             else:
                 entry["fb"].replay()
-                if dist_on:
+                if entry.get("fb2") is not None:     # two-stage backward: deep buckets travel beside the shallow stage
+                    self.buckets.start_deep()
+                    entry["fb2"].replay()
+                    self.buckets.finish()
+                elif dist_on:
                     self.buckets.allreduce()
                 entry["up"].replay()
                 loss, spec, extras = entry["loss"], entry["spec"], entry["extras"]
@@ -439,22 +499,48 @@ class Trainer:
                 torch._foreach_add_(live, 1)
         return dict(loss=loss, spec_cam=spec, grad_sumsq=self.sumsq, **extras)
 
+    def _eager_step(self, st, st_semi, two):
+        if two:
+            loss, spec = self._fwd_bwd_deep(st)
+            self.buckets.start_deep()
+            self._bwd_shallow()
+            self.buckets.finish()
+        else:
+            loss, spec = self._fwd_bwd(st, st_semi)
+            if self.world > 1:
+                self.buckets.allreduce()
+        self._update()
+        return loss, spec
+
     def _capture(self, key, st):
         entry = dict(stage=0)
         self._graphs[key] = entry
         return entry
 
-    def _do_capture(self, entry, st, st_semi=None):
+    def _do_capture(self, entry, st, st_semi=None, two=False):
         torch.cuda.synchronize()
         pool = torch.cuda.graph_pool_handle()
         n0 = L.launches
-        fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(fb, pool=pool):
-            loss, spec = self._fwd_bwd(st, st_semi)
+        fb, fb2 = torch.cuda.CUDAGraph(), None
+        if two:
+            with torch.cuda.graph(fb, pool=pool):
+                loss, spec = self._fwd_bwd_deep(st)
+            fb2 = torch.cuda.CUDAGraph()
+            # the grids of the shallow stage leave the communication SMs free: its kernels run beside the NCCL
+            # kernels of the deep buckets
+            L.call("b2_set_sm_reserve", int(self.comm_sms))
+            try:
+                with torch.cuda.graph(fb2, pool=pool):
+                    self._bwd_shallow()
+            finally:
+                L.call("b2_set_sm_reserve", 0)
+        else:
+            with torch.cuda.graph(fb, pool=pool):
+                loss, spec = self._fwd_bwd(st, st_semi)
         up = torch.cuda.CUDAGraph()
         with torch.cuda.graph(up, pool=pool):
             self._update()
-        entry.update(fb=fb, up=up, loss=loss, spec=spec, extras=self._extras)
+        entry.update(fb=fb, fb2=fb2, up=up, loss=loss, spec=spec, extras=self._extras)
         self.launches_per_step = L.launches - n0     # libb2pose kernels recorded into the two graphs
         # the capture itself did not execute: the grads in the flat buffer are from the last eager
         # warm-up step and have been consumed already, nothing to redo.

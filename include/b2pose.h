@@ -69,6 +69,12 @@ typedef struct B2ConvDesc {
 } B2ConvDesc;
 
 int b2_abi_version(void);
+/* Leave `sms` streaming multiprocessors free in every grid launched from now on (0 = use the whole device).  For
+ * callers that run other kernels beside this library's persistent one-CTA-per-SM grids -- the NCCL kernels of a
+ * gradient all-reduce overlapped with backward (the reference exchanges gradients inside nn.DataParallel,
+ * depth_main.py:72).  Process-wide; takes effect at the next launch (captured CUDA graphs keep the grids they were
+ * captured with). */
+int b2_set_sm_reserve(int32_t sms);
 const char* b2_last_error(void);
 /* 1 if the bf16 tensor-core (tcgen05) kernel will be used for this descriptor and op
  * (0 = fprop, 1 = dgrad, 2 = wgrad), 0 if the FFMA kernel will. */
@@ -128,6 +134,9 @@ int b2_nhwc_to_nchw(const void* in, float* out, int32_t N, int32_t C, int32_t H,
                     void* stream);
 /* dst = (dtype) src, elementwise fp32 -> bf16 (weight shadow copies) */
 int b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* dst = (float) src, elementwise bf16 -> fp32 (gradients exchanged between ranks as bf16: the all-reduce behind
+ * nn.DataParallel's gather, depth_main.py:72, moves half the bytes) */
+int b2_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
 
 /* ---- BatchNorm2d (+ReLU, +residual, +veil) --------------------------------------------
  * replaces nn.BatchNorm2d / F.relu / residual add in the blocks, partial_depthnet.py:143-157,

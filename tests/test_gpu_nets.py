@@ -123,25 +123,28 @@ def test_net_bf16(b2pose, dev, golden_dir, tag):
         z_eval, _ = forward(net, kind, cfg, batch)
     assert z_eval.dtype == torch.bfloat16
     assert rel_err(z_eval, g[f"{tag}_z_eval"]) < 2e-2
-    net.train()
+    # Training step: the fp32 fixture is not a meaningful reference for bf16 training-mode numbers (training-mode
+    # BatchNorm amplifies rounding ~200x through ResNet-50, tests/golden/bf16_sensitivity.npz), so the step is compared
+    # with the oracle under the same bf16 storage contract, on bf16-rounded filters and inputs; the per-layer bounds
+    # (2e-2 forward, 3e-2 backward) are in test_gpu_bf16_blocks.py, the full-size step in test_gpu_bf16_step.py.
+    sd = po.init_state(kind, model, cfg, seed=11)
+    sd = {k: (v.bfloat16().float() if v.dim() == 4 else v) for k, v in sd.items()}
+    hb = po.synth_batch(N, side, J, seed=3, invalid_frac=0.25)
+    hb = (hb[0].bfloat16().float(), hb[1].bfloat16().float(), hb[2], hb[3])
+    orc = po.StepOracle({k: v.clone() for k, v in sd.items()}, kind, model, cfg, key_index=J - 1, act_round=po.round_bf16)
+    loss_o, gn_o, spec_o, _ = orc.step(hb)
+    net = getattr(getattr(b2pose, kind), model)(cfg, False)
+    net.load_state_dict(sd)
+    net = net.to(dev).train()
     trainer = b2pose.Trainer(targs(b2pose, kind, model, cfg, half_acc=True), net, dict(key_index=J - 1),
                              use_graph=False)
-    out = trainer.train_step(batch)
-    # Train-mode loss on this tiny fixture (batch 2: BatchNorm over 32 values per channel in layer4) is
-    # chaotic in the last bits of the statistics: the deterministic slot path (B2POSE_BN_TOTALS=0) lands
-    # 0.3-1.5 % from the fp32 golden loss, the default totals path (fp32 reduction order varies run to run)
-    # was observed between 0.5 and 3.1 % over repeated runs, so the bound is 5 % here; eval-mode outputs above
-    # are held to the 2e-2 of the contract, full-size steps to tighter bounds in test_gpu_fullsize.py.
-    assert abs(float(out["loss"]) - g[f"{tag}_loss"][0]) / g[f"{tag}_loss"][0] < 5e-2
-    # bf16 carries ~3 significant digits and train-mode BN over a batch of 2 (32 values per channel
-    # in layer4) amplifies the rounding noise, so joints (range 2000 mm) are held to a loose bound on
-    # this tiny fixture; the 0.1 mm bound is asserted in fp32 above.
+    out = trainer.train_step(tuple(t.to(dev) for t in hb))
     spec = out["spec_cam"].cpu().numpy()
-    true_cam, valid = batch[2].cpu().numpy(), batch[3].cpu().numpy()
-    print(tag, "bf16 loss", float(out["loss"]), "golden", g[f"{tag}_loss"][0], "max|dspec| mm", np.abs(spec - g[f"{tag}_spec"]).max(),
-          "mpjpe", po.mpjpe(spec, true_cam, valid), po.mpjpe(g[f"{tag}_spec"], true_cam, valid))
-    assert abs(po.mpjpe(spec, true_cam, valid) - po.mpjpe(g[f"{tag}_spec"], true_cam, valid)) < 20.0
-    assert np.abs(spec - g[f"{tag}_spec"]).max() < 150.0
+    true_cam, valid = hb[2].numpy(), hb[3].numpy()
+    dm = abs(po.mpjpe(spec, true_cam, valid) - po.mpjpe(spec_o.numpy(), true_cam, valid))
+    print(tag, "bf16 loss", float(out["loss"]), "contract oracle", loss_o, "|dMPJPE| mm", dm)
+    assert abs(float(out["loss"]) - loss_o) / loss_o < 1e-2
+    assert dm < 10.0
 
 
 def test_graph_replay_matches_eager(b2pose, dev):
