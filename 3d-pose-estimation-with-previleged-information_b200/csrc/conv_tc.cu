@@ -242,6 +242,8 @@ struct FpropParams {
   int BN;                                              // output channels per tile (multiple of 16, <= 256)
   int cblocks, kblocks;                                // C/64, taps*C/64
   int stages, tmem_cols;
+  int b_resident;                                      // the whole filter (kblocks slices of BN rows) stays in shared memory
+  int n_staging;                                       // 16 KB output staging buffers of the TMA-store epilogue (<= kStaging)
   int scale_mode;                                      // 0 none, 1 partial-conv ratio from mask_in, 2 row_scale[]
   int mask_R, mask_S, mask_stride, mask_pad, mask_dil, mask_H, mask_W;   // window geometry for mode 1
   const float* mask_in;
@@ -251,6 +253,7 @@ struct FpropParams {
   float* ratio_out;
   bf16* out;
   int pad_w;                                           // horizontal padding (== pad except in strided dgrad classes)
+  int stride_w;                                        // horizontal stride (== stride except for the window-map stems)
   int out_stride_sp, out_off_h, out_off_w;             // strided dgrad: row (oh, ow) is stored at (oh*sp+off_h, ow*sp+off_w)
   int out_H, out_W;                                    // spatial size of the tensor written
   int tma_store;                                       // epilogue: smem-staged TMA store (+ fused BN statistics)
@@ -261,7 +264,7 @@ struct FpropParams {
 };
 
 struct __align__(8) PipeBars {
-  uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
+  uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2], bfull;
   uint32_t tmem_base;
 };
 
@@ -273,10 +276,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // 1024-byte alignment for the swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
-  const uint32_t stage_bytes = kABytes + b_bytes;
-  // layout: [stages][A|B] | kStaging x 16 KB output staging (TMA-store epilogue) | barriers | fp32 statistics [2*K]
-  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
-  PipeBars* bars = reinterpret_cast<PipeBars*>(staging + (p.tma_store ? kStaging * kABytes : 0));
+  const uint32_t stage_bytes = kABytes + (p.b_resident ? 0u : b_bytes);
+  // layout: [stages][A|B] | resident filter (b_resident: kblocks x B, the ring then holds A only) | kStaging x 16 KB
+  //         output staging (TMA-store epilogue) | barriers | fp32 statistics [2*K]
+  uint8_t* bres = smem + (size_t)p.stages * stage_bytes;
+  uint8_t* staging = bres + (p.b_resident ? (size_t)p.kblocks * b_bytes : 0);
+  PipeBars* bars = reinterpret_cast<PipeBars*>(staging + (p.tma_store ? p.n_staging * kABytes : 0));
   float* s_stats = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~(uintptr_t)15);
   if (p.bn_sums)      // [8 epilogue warps][2*K]: warp-private partials, no shared atomics
     for (int i = threadIdx.x; i < 16 * p.K; i += kConvThreads) s_stats[i] = 0.f;
@@ -288,6 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 8); }
+    mbar_init(&bars->bfull, 1);
     fence_barrier_init();
     prefetch_map(&map_a);
     prefetch_map(&map_b);
@@ -305,12 +311,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Converged warp; elect.sync inside produce_fused picks the issuing lane.  No divisions in the loop: (tap row,
     // tap column, channel block) advance as counters.
     const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BNI) * kBlockK * 2;
+    if (p.b_resident && lane == 0 && !(p.debug & 24)) {
+      // the filter is the same for every tile of this CTA (tiles_k == 1): fetch it once
+      mbar_expect_tx(&bars->bfull, (uint32_t)p.kblocks * b_bytes);
+      int bcol = 0, cb = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        tma_load_2d(smem_u32(bres + (size_t)kb * b_bytes), &map_b, &bars->bfull, bcol, 0);
+        bcol += kBlockK;
+        if (++cb == p.cblocks) { cb = 0; bcol += p.C - p.cblocks * kBlockK; }
+      }
+    }
+    __syncwarp();
+    const uint32_t stage_flags = p.b_resident ? 0u : kLoadB;
+    const uint32_t stage_tx = a_box_bytes + (p.b_resident ? 0u : b_bytes);
     int stage = 0;
     uint32_t phase = 0, empty_ready = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int kt = tile % p.tiles_k, mt = tile / p.tiles_k;
       const int wi = mt % p.tiles_w, hi = (mt / p.tiles_w) % p.tiles_h, ni = mt / (p.tiles_w * p.tiles_h);
-      const int iw0 = wi * p.BW * p.stride - p.pad_w, ih0 = hi * p.BH * p.stride - p.pad, n0 = ni * p.BNI;
+      const int iw0 = wi * p.BW * p.stride_w - p.pad_w, ih0 = hi * p.BH * p.stride - p.pad, n0 = ni * p.BNI;
       const bool more_tiles = tile + (int)gridDim.x < total_tiles;
       int r = 0, s = 0, cb = 0, bcol = 0;                 // bcol = tap * C + cb * 64
       for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -332,8 +351,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           __syncwarp();
         } else {
           const bool has_next = kb + 1 < p.kblocks || more_tiles;
-          empty_ready = produce_fused((has_next ? 1u : 0u) | kLoadB, smem_u32(&bars->empty[nstage]), nphase ^ 1,
-                                      smem_u32(&bars->full[stage]), a_box_bytes + b_bytes, sa, &map_a, cb * kBlockK,
+          empty_ready = produce_fused((has_next ? 1u : 0u) | stage_flags, smem_u32(&bars->empty[nstage]), nphase ^ 1,
+                                      smem_u32(&bars->full[stage]), stage_tx, sa, &map_a, cb * kBlockK,
                                       iw0 + s * p.dil, ih0 + r * p.dil, n0, sa + kABytes, &map_b, bcol, kt * p.BN);
         }
         bcol += kBlockK;
@@ -356,6 +375,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t phase = 0;
     int local = 0;
     uint32_t full_ready = 0, acc_ready = 0;
+    if (p.b_resident && !(p.debug & 24) && blockIdx.x < total_tiles) mbar_wait(&bars->bfull, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -375,7 +395,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t flags = ((!last || more_tiles) ? kPoll1 : 0u) | ((last && more_tiles) ? kPoll2 : 0u) | kCommit1 |
                                (last ? kCommit2 : 0u);
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        mma4_fused(tmem_d, smem_desc(sa, 0, 1024), smem_desc(sa + kABytes, 0, 1024), 2ull, idesc, (uint32_t)kb, flags,
+        const uint32_t sb = p.b_resident ? smem_u32(bres + (size_t)kb * b_bytes) : sa + kABytes;
+        mma4_fused(tmem_d, smem_desc(sa, 0, 1024), smem_desc(sb, 0, 1024), 2ull, idesc, (uint32_t)kb, flags,
                    smem_u32(&bars->full[nstage]), nphase, smem_u32(&bars->tempty[nacc]), nacc_parity,
                    smem_u32(&bars->empty[stage]), smem_u32(&bars->tfull[acc]), full_ready, acc_ready);
         stage = nstage;
@@ -393,7 +414,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row = q * 32 + lane;
     const int brick = p.BW * p.BH;
     const int groups = p.BN >> 6;
-    const int nsets = p.tma_store ? kStaging / groups : 1;      // staging sets of `groups` 16 KB buffers
+    const int nsets = p.tma_store ? p.n_staging / groups : 1;   // staging sets of `groups` 16 KB buffers
     uint64_t st_sum[2][4], st_sq[2][4];           // fused BatchNorm statistics (packed fp32x2), see below
 #pragma unroll
     for (int k = 0; k < 2; ++k)
@@ -621,6 +642,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // D[128 k, BNc c] accumulated in TMEM over the item's pixel bricks, then red.add into dw (fp32).
 struct WgradParams {
   int N, H, W, C, K, R, S, stride, pad, dil, Ho, Wo;
+  int stride_w, pad_w;             // horizontal stride / padding (== stride / pad except for the window-map stems)
   int BW, BH, BNI;                 // pixel brick per pipeline stage (BW*BH*BNI = 64 pixels incl. ragged rows)
   int tiles_w, tiles_h, tiles_n;   // bricks over the OUTPUT pixel space
   int BNc, ctiles, ktiles, splits; // columns per tap, ceil(C/BNc), ceil(K/128), pixel splits
@@ -695,7 +717,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint32_t fb = smem_u32(&bars->full[stage]);
-        const int xw0 = ow0 * p.stride - p.pad, xh0 = oh0 * p.stride - p.pad;
+        const int xw0 = ow0 * p.stride_w - p.pad_w, xh0 = oh0 * p.stride - p.pad;
         const bool has_next = b + 1 < b1 || more_items;
         // dy atoms: k channels [kt*128, +64) and [+64, +128); first x atom of the first tap
         empty_ready = produce_wgrad_fused(has_next ? 1u : 0u, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
@@ -890,63 +912,54 @@ im2col_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* 
   }
 }
 
-// ---- 7x7 stride-2 stem as a 4x4 stride-1 convolution over a space-to-depth view ------------------
-// xs[n, h', w', (a*2+b)*C + c] = x[n, 2h'+a-1, 2w'+b-1, c] (* mask), channels >= 4C are zero.  With
-// pad' = 1 the tap (t, a) of the 4x4 view is the original tap r = 2t + a (r = 7 does not exist: zero
-// weight), so no im2col matrix is ever materialised: the view is 1/10 of its size.
-__global__ void s2d_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ xs, int N,
-                           int H, int W, int C, int H2, int W2, int Cp) {
-  const int chunks = Cp >> 3;
-  const long long total = (long long)N * H2 * W2 * chunks;
+// ---- 7x7 stride-2 stems: TMA does the im2col -------------------------------------------------------------
+// The input is copied once into a zero-bordered 4-channel image xp[N][H+6][Wp][4] (8 bytes per pixel, 3 rows of border
+// above / below, 4 pixels left, >= 12 right).  For output pixel (oh, ow) and filter ROW r the seven taps (s, c) are the
+// contiguous pixels 2ow-3 .. 2ow+3 of padded row 2oh + r, i.e. bytes [16 ow + 8, 16 ow + 64) of that row: a tensor map
+// whose second dimension is the OUTPUT column with a 16-byte stride and whose innermost dimension is a 64-element
+// (128-byte, 16-pixel) window hands the tensor core an im2col row per output pixel without the matrix ever existing
+// (round 1 wrote N*Ho*Wo*152 bf16 = 319 MB to HBM and read it back, twice per step).  The layer then IS a convolution
+// with R = 7, S = 1, C = 64 for the generic kernels: window element j = 4 p + c holds pixel 2ow - 4 + p, channel c, so
+// the filter is laid out as Wk[k][r][j] = W[k][r][s = p - 1][c] (zero for p = 0, p > 7, c >= C).
+__global__ void vw_pad_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ xp, int N,
+                              int H, int W, int C, int Hp, int Wp) {
+  const long long total = (long long)N * Hp * Wp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % chunks);
-    const long long pix = i / chunks;
-    const int w2 = (int)(pix % W2);
-    const long long t = pix / W2;
-    const int h2 = (int)(t % H2), n = (int)(t / H2);
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int cc = ch * 8 + j;
-      float v = 0.f;
-      if (cc < 4 * C) {
-        const int ab = cc / C, c = cc - ab * C;
-        const int ih = 2 * h2 + (ab >> 1) - 1, iw = 2 * w2 + (ab & 1) - 1;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-          const long long ip = ((long long)n * H + ih) * W + iw;
-          v = __bfloat162float(x[ip * C + c]);
-          if (mask) v *= mask[ip];
-        }
-      }
-      f[j] = v;
+    const int wp = (int)(i % Wp);
+    const long long t = i / Wp;
+    const int hp = (int)(t % Hp), n = (int)(t / Hp);
+    const int h = hp - 3, w = wp - 4;
+    uint32_t lo = 0, hi = 0;
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const long long ip = ((long long)n * H + h) * W + w;
+      const float m = mask ? mask[ip] : 1.f;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < C; ++c) v[c] = __bfloat162float(x[ip * C + c]) * m;
+      lo = f32x2_to_bf16x2(v[0], v[1]);
+      hi = f32x2_to_bf16x2(v[2], v[3]);
     }
-    store8(xs + pix * Cp + ch * 8, f);
+    *reinterpret_cast<uint2*>(xp + i * 4) = make_uint2(lo, hi);
   }
 }
-// Ws[k][t][u][(a*2+b)*C + c] = W[k][2t+a][2u+b][c]  (zero where the 7x7 filter has no tap)
-__global__ void s2d_filter_kernel(const bf16* __restrict__ w, bf16* __restrict__ ws, int K, int C, int Cp) {
-  const int total = K * 16 * Cp;
+// Wk[k][r][4 p + c] = W[k][r][p - 1][c]
+__global__ void vw_filter_kernel(const bf16* __restrict__ w, bf16* __restrict__ wk, int K, int C) {
+  const int total = K * 7 * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int cc = i % Cp, tu = (i / Cp) % 16, k = i / (Cp * 16);
-    const int t = tu >> 2, u = tu & 3;
+    const int j = i & 63, r = (i >> 6) % 7, k = i / (7 * 64);
+    const int pp = j >> 2, c = j & 3, s2 = pp - 1;
     bf16 v = __float2bfloat16(0.f);
-    if (cc < 4 * C) {
-      const int ab = cc / C, c = cc - ab * C;
-      const int r = 2 * t + (ab >> 1), s2 = 2 * u + (ab & 1);
-      if (r < 7 && s2 < 7) v = w[((long long)k * 49 + r * 7 + s2) * C + c];
-    }
-    ws[i] = v;
+    if (s2 >= 0 && s2 < 7 && c < C) v = w[((long long)k * 49 + r * 7 + s2) * C + c];
+    wk[i] = v;
   }
 }
-// dw[k][r][s][c] += dWs[k][t][u][(a*2+b)*C + c],  r = 2t+a, s = 2u+b
-__global__ void s2d_unfilter_add_kernel(const float* __restrict__ dws, float* __restrict__ dw, int K, int C, int Cp) {
+// dw[k][r][s][c] += dWk[k][r][4 (s + 1) + c]
+__global__ void vw_unfilter_add_kernel(const float* __restrict__ dwk, float* __restrict__ dw, int K, int C) {
   const int total = K * 49 * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % C, rs = (i / C) % 49, k = i / (C * 49);
     const int r = rs / 7, s2 = rs - r * 7;
-    const int t = r >> 1, a2 = r & 1, u = s2 >> 1, b2 = s2 & 1;
-    dw[i] += dws[((long long)k * 16 + t * 4 + u) * Cp + (a2 * 2 + b2) * C + c];
+    dw[i] += dwk[((long long)k * 7 + r) * 64 + 4 * (s2 + 1) + c];
   }
 }
 
@@ -998,6 +1011,25 @@ int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, i
   B2_REQUIRE(r == CUDA_SUCCESS, B2_E_LAUNCH,
              "conv_tc: cuTensorMapEncodeTiled(activation N=%d H=%d W=%d C=%d box %dx%dx%d es=%d) failed: %d", N, H, W,
              C, bni, bh, bw, es, (int)r);
+  return B2_OK;
+}
+
+// 4-D window map over the zero-bordered stem input xp[N][Hp][Wp][4]: dims (64-element window, output column, padded
+// row, image), strides (16 B per output column, one padded row, one padded image); box (64, bw, 2 bh, bni) with element
+// stride 2 along the rows (vertical stride of the stem)
+int make_vw_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp, int Wo, int bw, int bh, int bni) {
+  EncodeTiledFn fn = encode_fn();
+  B2_REQUIRE(fn != nullptr, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Hp, (cuuint64_t)N};
+  cuuint64_t strides[3] = {16, (cuuint64_t)Wp * 8, (cuuint64_t)Hp * Wp * 8};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)(bh * 2), (cuuint32_t)bni};
+  cuuint32_t estr[4] = {1, 1, 2, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2_REQUIRE(r == CUDA_SUCCESS, B2_E_LAUNCH,
+             "conv_tc: cuTensorMapEncodeTiled(stem window map N=%d Hp=%d Wp=%d Wo=%d box %dx%dx%d) failed: %d", N, Hp, Wp,
+             Wo, bni, bh, bw, (int)r);
   return B2_OK;
 }
 
@@ -1062,6 +1094,7 @@ struct RunArgs {
   const void* filt; int K, R, S, stride, pad, dil, Ho, Wo;    // filt: [K][R*S*C] bf16
   void* out; int out_H, out_W, out_stride_sp, out_off_h, out_off_w;
   int pad_w, use_pad_w;                                        // pad_w is read only when use_pad_w != 0
+  int vw_hp, vw_wp;                                            // != 0: `act` is a window-map stem input (make_vw_map)
   int accumulate;                                              // dgrad: reduce-add into `out`
   float* bn_sums; bool* stats_fused; int bn_totals;           // optional fused BatchNorm statistics
   int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
@@ -1086,7 +1119,7 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.tiles_k = (a.K + p.BN - 1) / p.BN;
   p.cblocks = (a.C + kBlockK - 1) / kBlockK;      // a ragged last block is zero-filled by TMA on the A side
   p.kblocks = a.R * a.S * p.cblocks;
-  const int stage_bytes = (int)kABytes + p.BN * kBlockK * 2;
+  int stage_bytes = (int)kABytes + p.BN * kBlockK * 2;
   static const bool no_tma_store = getenv("B2POSE_TC_NO_TMA_STORE") != nullptr;      // tuning switches
   static const bool no_fused_stats = getenv("B2POSE_TC_NO_FUSED_STATS") != nullptr;
   p.tma_store = (p.BN % 64 == 0 && a.out_stride_sp == 1 && !a.bias && !no_tma_store) ? 1 : 0;   // bias: direct-store path
@@ -1099,7 +1132,21 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.bn_sums = (p.tma_store && a.bn_sums && a.K <= 256 && p.tiles_k == 1 && !no_fused_stats) ? a.bn_sums : nullptr;
   p.bn_totals = a.bn_totals;
   if (a.stats_fused) *a.stats_fused = p.bn_sums != nullptr;
-  const int extra = (p.tma_store ? kStaging * (int)kABytes : 0) + (p.bn_sums ? 64 * a.K : 0);
+  p.n_staging = kStaging;
+  int extra = (p.bn_sums ? 64 * a.K : 0);
+  // Filter resident in shared memory when one channel tile covers K and the whole filter is small (layer1-type layers,
+  // the stems): the ring then carries activation tiles only -- a third to two thirds less L2 -> SM traffic per tile and
+  // a deeper ring, which is what bounds these layers (B2POSE_TC_B_RESIDENT=0 disables)
+  static const bool allow_resident = !(getenv("B2POSE_TC_B_RESIDENT") && atoi(getenv("B2POSE_TC_B_RESIDENT")) == 0);
+  const int filt_bytes = p.kblocks * p.BN * kBlockK * 2;
+  p.b_resident = (allow_resident && p.tiles_k == 1 && filt_bytes <= 96 * 1024 &&
+                  (long long)p.tiles_w * p.tiles_h * p.tiles_n >= 2LL * b2_num_sms()) ? 1 : 0;
+  if (p.b_resident) {
+    stage_bytes = (int)kABytes;
+    extra += filt_bytes;
+    if (p.BN <= 64) p.n_staging = 2;           // two sets of one buffer: room for two more activation stages
+  }
+  extra += p.tma_store ? p.n_staging * (int)kABytes : 0;
   int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars) - extra) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   B2_REQUIRE(stages >= 2, B2_E_UNSUPPORTED, "conv_tc: not enough shared memory for two stages");
@@ -1112,8 +1159,10 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.out_stride_sp = a.out_stride_sp; p.out_H = a.out_H; p.out_W = a.out_W;
   p.out_off_h = a.out_off_h; p.out_off_w = a.out_off_w;
   p.pad_w = a.use_pad_w ? a.pad_w : a.pad;
+  p.stride_w = a.vw_hp ? 1 : a.stride;
   CUtensorMap ma, mb, mo;
-  int rc = make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
+  int rc = a.vw_hp ? make_vw_map(&ma, a.act, a.N, a.vw_hp, a.vw_wp, a.Wo, p.BW, p.BH, p.BNI)
+                   : make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
   if (rc) return rc;
   rc = make_mat_map(&mb, a.filt, a.K, (long long)a.R * a.S * a.C, p.BN);
   if (rc) return rc;
@@ -1154,30 +1203,23 @@ namespace {
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 inline bool is_stem(const B2ConvDesc* d) { return d->C <= 4 && d->R * d->S * d->C >= 32; }
-// the networks' stems: 7x7, stride 2, pad 3 -> 4x4 stride-1 convolution over the space-to-depth view
-inline bool is_s2d_stem(const B2ConvDesc* d) {
-  // (C >= 3: for one input channel the im2col matrix is only 56 columns wide and measures faster)
-  // Measured (N64, 256x256x3 -> 64): space-to-depth 0.40 ms fprop / 0.57 ms wgrad, im2col + GEMM 0.29 / 0.39 ms
-  // (16 thin k-steps per tile versus 3 dense ones), so the im2col route is the default; B2POSE_STEM_S2D=1
-  // selects the space-to-depth route.
-  static const int mode = getenv("B2POSE_STEM_S2D") ? atoi(getenv("B2POSE_STEM_S2D")) : 0;
-  return mode != 0 && is_stem(d) && d->C >= 3 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 &&
-         d->dil == 1;
+// the networks' stems (7x7, stride 2, pad 3): window-map route, see vw_pad_kernel.  B2POSE_STEM_IM2COL=1 selects round
+// 1's materialised im2col matrix + GEMM (kept for the other thin-input geometries) for A/B measurements.
+inline bool is_vw_stem(const B2ConvDesc* d) {
+  static const int im2col = getenv("B2POSE_STEM_IM2COL") ? atoi(getenv("B2POSE_STEM_IM2COL")) : 0;
+  return !im2col && is_stem(d) && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->dil == 1;
 }
-inline int s2d_cp(const B2ConvDesc* d) { return (4 * d->C + 7) / 8 * 8; }
-inline int s2d_h2(const B2ConvDesc* d) { return (d->H + 2) / 2; }
-inline int s2d_w2(const B2ConvDesc* d) { return (d->W + 2) / 2; }
-inline size_t s2d_view_bytes(const B2ConvDesc* d) {
-  return (size_t)d->N * s2d_h2(d) * s2d_w2(d) * s2d_cp(d) * 2;
-}
+inline int vw_hp(const B2ConvDesc* d) { return d->H + 6; }
+inline int vw_wp(const B2ConvDesc* d) { return (d->W + 17) / 2 * 2; }      // even (16-byte row pitch), >= W + 16
+inline size_t vw_view_bytes(const B2ConvDesc* d) { return (size_t)d->N * vw_hp(d) * vw_wp(d) * 8; }
 inline int stem_kpad(const B2ConvDesc* d) { return (d->R * d->S * d->C + 7) / 8 * 8; }
 
-int launch_s2d(const B2ConvDesc* d, const void* x, const float* mask, bf16* xs, cudaStream_t st) {
-  const int cp = s2d_cp(d), h2 = s2d_h2(d), w2 = s2d_w2(d);
-  const long long total = (long long)d->N * h2 * w2 * (cp / 8);
+int launch_vw_pad(const B2ConvDesc* d, const void* x, const float* mask, bf16* xp, cudaStream_t st) {
+  const long long total = (long long)d->N * vw_hp(d) * vw_wp(d);
   long long want = (total + 255) / 256, cap = (long long)b2_num_sms() * 16;
-  s2d_kernel<<<(int)(want > cap ? cap : want), 256, 0, st>>>((const bf16*)x, mask, xs, d->N, d->H, d->W, d->C, h2, w2, cp);
-  B2_LAUNCH_CHECK("s2d");
+  vw_pad_kernel<<<(int)(want > cap ? cap : want), 256, 0, st>>>((const bf16*)x, mask, xp, d->N, d->H, d->W, d->C, vw_hp(d),
+                                                              vw_wp(d));
+  B2_LAUNCH_CHECK("vw_pad");
   return B2_OK;
 }
 
@@ -1219,9 +1261,10 @@ size_t conv_tc_workspace_bytes(const B2ConvDesc* d, int op) {
   size_t ws = 0;
   const bool partial = d->flags & B2_CONV_PARTIAL;
   const size_t dy_bytes = align256((size_t)d->N * d->Ho * d->Wo * d->K * 2);
-  if (is_s2d_stem(d)) {
-    ws += align256(s2d_view_bytes(d));                                    // space-to-depth view
-    ws += align256((size_t)d->K * 16 * s2d_cp(d) * (op == 2 ? 4 : 2));    // 4x4 filter / its gradient
+  if (is_vw_stem(d)) {
+    ws += align256(vw_view_bytes(d));                                     // zero-bordered 4-channel input
+    ws += align256((size_t)d->K * 7 * 64 * (op == 2 ? 4 : 2));            // window-layout filter / its gradient
+    if (op == 0 && partial) ws += align256((size_t)d->N * d->Ho * d->Wo * 4);   // renormalisation ratio
     if (op == 2 && partial && !(d->flags & B2_CONV_DY_PRESCALED)) ws += dy_bytes;
     return ws;
   }
@@ -1248,16 +1291,25 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   const float* stem_ratio = nullptr;
   a.act = x; a.N = d->N; a.H = d->H; a.W = d->W; a.C = d->C;
   a.filt = w; a.K = d->K; a.R = d->R; a.S = d->S; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
-  if (is_s2d_stem(d)) {
-    const int cp = s2d_cp(d);
-    bf16* xs = (bf16*)workspace;
-    bf16* wsf = (bf16*)((uint8_t*)workspace + align256(s2d_view_bytes(d)));
-    int rc = launch_s2d(d, x, (partial && !premasked) ? mask_in : nullptr, xs, st);
+  if (is_vw_stem(d)) {
+    bf16* xp = (bf16*)workspace;
+    bf16* wk = (bf16*)((uint8_t*)workspace + align256(vw_view_bytes(d)));
+    // B2_CONV_X_PREMASKED: the caller's x is zero wherever the mask is (network stems: veil = depth != 0)
+    int rc = launch_vw_pad(d, x, (partial && !premasked) ? mask_in : nullptr, xp, st);
     if (rc) return rc;
-    s2d_filter_kernel<<<(d->K * 16 * cp + 255) / 256, 256, 0, st>>>((const bf16*)w, wsf, d->K, d->C, cp);
-    B2_LAUNCH_CHECK("s2d_filter");
-    a.act = xs; a.H = s2d_h2(d); a.W = s2d_w2(d); a.C = cp; a.filt = wsf; a.R = 4; a.S = 4; a.stride = 1; a.pad = 1;
-    a.dil = 1;
+    vw_filter_kernel<<<(d->K * 7 * 64 + 255) / 256, 256, 0, st>>>((const bf16*)w, wk, d->K, d->C);
+    B2_LAUNCH_CHECK("vw_filter");
+    a.act = xp; a.vw_hp = vw_hp(d); a.vw_wp = vw_wp(d);
+    a.H = vw_hp(d); a.W = d->Wo; a.C = 64; a.filt = wk; a.R = 7; a.S = 1; a.stride = 2; a.pad = 0; a.dil = 1;
+    a.pad_w = 0; a.use_pad_w = 1;
+    if (partial) {
+      // a 7x7 window is 49 mask loads per output pixel: do the mask algebra once in its own small
+      // kernel and let the convolution epilogue read the ratio as a per-row scale
+      float* rbuf = ratio_out ? ratio_out : (float*)((uint8_t*)wk + align256((size_t)d->K * 7 * 64 * 2));
+      rc = b2_pconv_mask_update(d, mask_in, mask_out, rbuf, (void*)st);
+      if (rc) return rc;
+      stem_ratio = rbuf;
+    }
   } else if (is_stem(d)) {
     const int kpad = stem_kpad(d);
     bf16* col = (bf16*)workspace;
@@ -1412,20 +1464,21 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   float* dw_out = dw;
   float* dwp = nullptr;
   int kpad = 0;
-  bool s2d = false;
-  if (is_s2d_stem(d)) {
-    s2d = true;
-    kpad = s2d_cp(d);
-    bf16* xs = (bf16*)ws;
-    ws += align256(s2d_view_bytes(d));
+  bool vw = false;
+  if (is_vw_stem(d)) {
+    vw = true;
+    bf16* xp = (bf16*)ws;
+    ws += align256(vw_view_bytes(d));
     dwp = (float*)ws;
-    ws += align256((size_t)d->K * 16 * kpad * 4);
-    int rc = launch_s2d(d, x, (partial && !premasked) ? mask_in : nullptr, xs, st);
-    if (rc) return rc;
-    cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)d->K * 16 * kpad * 4, st);
+    ws += align256((size_t)d->K * 7 * 64 * 4);
+    if (!(d->flags & B2_CONV_WS_HAS_COL)) {       // (else: the caller kept the fprop workspace, xp is in it)
+      int rc = launch_vw_pad(d, x, (partial && !premasked) ? mask_in : nullptr, xp, st);
+      if (rc) return rc;
+    }
+    cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)d->K * 7 * 64 * 4, st);
     B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc_wgrad: memset failed: %s", cudaGetErrorString(e));
-    x = xs;
-    g.H = s2d_h2(d); g.W = s2d_w2(d); g.C = kpad; g.R = 4; g.S = 4; g.stride = 1; g.pad = 1; g.dil = 1;
+    x = xp;
+    g.H = vw_hp(d); g.W = d->Wo; g.C = 64; g.R = 7; g.S = 1; g.stride = 2; g.pad = 0; g.dil = 1;
     dw_out = dwp;
   } else if (is_stem(d)) {
     kpad = stem_kpad(d);
@@ -1454,6 +1507,7 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   WgradParams p;
   p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.K = d->K; p.R = d->R; p.S = d->S;
   p.stride = d->stride; p.pad = d->pad; p.dil = d->dil; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.stride_w = vw ? 1 : d->stride; p.pad_w = vw ? 0 : d->pad;
   // bricks of exactly 64 pixel slots over the output space (rows of 128 B each; ragged parts zero-filled)
   {
     double best = -1;
@@ -1501,7 +1555,8 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   CUtensorMap mdy, mx;
   int rc = make_act_map(&mdy, dys, d->N, d->Ho, d->Wo, d->K, p.BW, p.BH, p.BNI, 1);
   if (rc) return rc;
-  rc = make_act_map(&mx, x, d->N, d->H, d->W, d->C, p.BW, p.BH, p.BNI, d->stride);
+  rc = vw ? make_vw_map(&mx, x, d->N, vw_hp(d0), vw_wp(d0), d->Wo, p.BW, p.BH, p.BNI)
+          : make_act_map(&mx, x, d->N, d->H, d->W, d->C, p.BW, p.BH, p.BNI, d->stride);
   if (rc) return rc;
   const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024;
   static bool configured = false;
@@ -1515,9 +1570,9 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   cudaError_t le = launch_pdl(wgrad_tc_kernel, dim3(grid), dim3(kThreads), smem, st, mdy, mx, p);
   B2_REQUIRE(le == cudaSuccess, B2_E_LAUNCH, "wgrad_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   B2_LAUNCH_CHECK("wgrad_tc_kernel");
-  if (dwp && s2d) {
-    s2d_unfilter_add_kernel<<<(d0->K * 49 * d0->C + 255) / 256, 256, 0, st>>>(dwp, dw, d0->K, d0->C, kpad);
-    B2_LAUNCH_CHECK("s2d_unfilter_add");
+  if (dwp && vw) {
+    vw_unfilter_add_kernel<<<(d0->K * 49 * d0->C + 255) / 256, 256, 0, st>>>(dwp, dw, d0->K, d0->C);
+    B2_LAUNCH_CHECK("vw_unfilter_add");
   } else if (dwp) {
     const int rsc = d0->R * d0->S * d0->C;
     unpad_add_kernel<<<(d0->K * rsc + 255) / 256, 256, 0, st>>>(dwp, dw, d0->K, rsc, kpad);
