@@ -49,6 +49,25 @@ __device__ __forceinline__ void s_bulk_load(void* dst, const void* src, uint32_t
                : "memory");
 }
 
+__device__ __forceinline__ void s_bulk_load_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)), "l"(pol)
+               : "memory");
+}
+// L2 eviction priority of the streamed inputs (B2POSE_BN_L2HINT=1).  The same tensors are read twice back to back --
+// statistics / gradient sums first, then the apply pass -- and most of them are smaller than the 126 MB L2: the first
+// pass asks the L2 to keep its lines (evict_last), the second pass marks them dead (evict_first).
+__device__ __forceinline__ uint64_t l2_policy(int hint) {
+  uint64_t pol = 0;
+  if (hint == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (hint == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+inline int l2_hint_mode() {
+  static const int v = getenv("B2POSE_BN_L2HINT") ? atoi(getenv("B2POSE_BN_L2HINT")) : 0;
+  return v;
+}
+
 // Ring of kStagesS stages, NIN input streams each.  `issue(c)` is called by thread 0.
 template <int NIN>
 struct Ring {
@@ -56,6 +75,7 @@ struct Ring {
   uint64_t* full;    // [kStagesS]
   const uint8_t* src[NIN];
   long long total_bytes;
+  uint64_t policy = 0;             // L2 cache-hint policy of the loads (0: none)
   const uint8_t* bits = nullptr;   // optional 1-bit-per-element side stream (ReLU gate): kChunkBytes / 16 bytes per chunk
   uint8_t* bits_buf = nullptr;     // [kStagesS][kChunkBytes / 16]
 
@@ -66,8 +86,10 @@ struct Ring {
     const uint32_t gb = bits ? ((bytes >> 4) + 15u) & ~15u : 0u;       // bulk copies move multiples of 16 bytes
     s_mbar_expect(&full[stage], bytes * NIN + gb);
 #pragma unroll
-    for (int i = 0; i < NIN; ++i)
-      s_bulk_load(buf + ((size_t)stage * NIN + i) * kChunkBytes, src[i] + off, bytes, &full[stage]);
+    for (int i = 0; i < NIN; ++i) {
+      if (policy) s_bulk_load_hint(buf + ((size_t)stage * NIN + i) * kChunkBytes, src[i] + off, bytes, &full[stage], policy);
+      else s_bulk_load(buf + ((size_t)stage * NIN + i) * kChunkBytes, src[i] + off, bytes, &full[stage]);
+    }
     if (bits) s_bulk_load(bits_buf + (size_t)stage * (kChunkBytes / 16), bits + (off >> 4), gb, &full[stage]);
   }
   __device__ __forceinline__ const bf16* data(int stage, int i) const {
@@ -273,6 +295,7 @@ struct BwdArgs {
   bf16 *dy, *d_residual;
   float* partials;
   int totals;                  // reduce: partials is a pre-zeroed float[2C] (atomic adds)
+  int l2_hint;                 // 0 none, 1 keep the inputs in L2 (reduce pass), 2 inputs are dead after this pass
   float *dgamma, *dbeta;       // apply: block 0 accumulates the affine gradients from gsum
   long long total_elems, rows;
   int C;
@@ -295,6 +318,7 @@ __global__ void __launch_bounds__(kThreadsS, 3) bwd_stream_kernel(const BwdArgs 
     ring.bits = a.gate;
     ring.bits_buf = smem + (size_t)kStagesS * NIN * kChunkBytes + 64 + (MODE == 0 ? 2 * kThreadsS * 8 * sizeof(float) : 0);
   }
+  ring.policy = l2_policy(a.l2_hint);
   ring_setup(ring, smem, a.total_elems * 2);
   float* red = reinterpret_cast<float*>(smem + (size_t)kStagesS * NIN * kChunkBytes + 64);
   const int C = a.C, CV = C >> 3, cv = threadIdx.x % CV, logC = 31 - __clz(C);
@@ -472,6 +496,8 @@ int bn_stream_bwd_reduce(const void* dz, const void* z, const void* y, const flo
                          int totals, const uint8_t* gate, int64_t rows, int C, cudaStream_t st) {
   BwdArgs a = make_bwd(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, rows, C);
   a.partials = partials; a.totals = totals; a.gate = gate;
+  // keep dz / y in L2 for the apply pass when both fit beside the rest of the working set
+  a.l2_hint = (l2_hint_mode() && (long long)rows * C * 4 <= 96LL << 20) ? 1 : 0;
   const int gsrc = !relu ? 0 : (gate ? 2 : (z ? 1 : 0));
   const size_t sh = smem_bytes(gsrc == 1 ? 3 : 2, true, gsrc == 2);
   const int grid = stream_grid(rows * C, 2, true);
@@ -497,6 +523,7 @@ int bn_stream_bwd_apply(const void* dz, const void* z, const void* y, const floa
   BwdArgs a = make_bwd(dz, z, y, mean, invstd, gamma, beta, row_mask, relu, rows, C);
   a.dgamma = dgamma; a.dbeta = dbeta; a.gate = gate;
   a.gsum = gsum; a.row_scale = row_scale; a.training = training; a.dy = (bf16*)dy; a.d_residual = (bf16*)d_residual;
+  a.l2_hint = l2_hint_mode() ? 2 : 0;            // dz and y are dead after this pass
   const int gsrc = !relu ? 0 : (gate ? 2 : (z ? 1 : 0));
   const size_t sh = smem_bytes(gsrc == 1 ? 3 : 2, false, gsrc == 2);
   const int grid = stream_grid(rows * C, 3, false);

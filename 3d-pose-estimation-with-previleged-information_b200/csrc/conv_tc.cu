@@ -221,6 +221,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, 128-byte swizzle (layout type 2), descriptor version 1
@@ -420,42 +428,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int k = 0; k < 2; ++k)
 #pragma unroll
       for (int e = 0; e < 4; ++e) st_sum[k][e] = st_sq[k][e] = 0ull;
+    // Row geometry of this thread in a tile, and the mask values its renormalisation ratio needs.  The mask loads of
+    // tile i + 1 are ISSUED while tile i is processed and consumed at the top of the next iteration (ncu: the
+    // dependent add right behind the load was 9 % of all stall samples of the partial 1x1 layers).
+    struct RowGeo { int kt, wi, hi, ni, n, oh, ow; bool valid; long long pix, opix; };
+    const int row_bn = row / brick, row_rem = row - row_bn * brick;
+    const int row_bh = row_rem / p.BW, row_bw = row_rem - row_bh * p.BW;
+    auto geometry = [&](int tile) {
+      RowGeo g;
+      g.kt = tile % p.tiles_k;
+      const int mt = tile / p.tiles_k;
+      g.wi = mt % p.tiles_w; g.hi = (mt / p.tiles_w) % p.tiles_h; g.ni = mt / (p.tiles_w * p.tiles_h);
+      g.n = g.ni * p.BNI + row_bn; g.oh = g.hi * p.BH + row_bh; g.ow = g.wi * p.BW + row_bw;
+      const int sh = g.oh * p.out_stride_sp + p.out_off_h, sw = g.ow * p.out_stride_sp + p.out_off_w;
+      g.valid = (row_bn < p.BNI) && (g.n < p.N) && (g.oh < p.Ho) && (g.ow < p.Wo) && (sh < p.out_H) && (sw < p.out_W);
+      g.pix = ((long long)g.n * p.Ho + g.oh) * p.Wo + g.ow;
+      g.opix = ((long long)g.n * p.out_H + sh) * p.out_W + sw;
+      return g;
+    };
+    const int mask_taps = p.mask_R * p.mask_S;
+    const bool prefetch_mask = p.scale_mode == 2 || (p.scale_mode == 1 && mask_taps <= 9);
+    auto load_mask = [&](const RowGeo& g, float (&mv)[9]) {       // issue only: nothing here depends on the values
+#pragma unroll
+      for (int t = 0; t < 9; ++t) mv[t] = 0.f;
+      if (!g.valid || !prefetch_mask) return;
+      if (p.scale_mode == 2) { mv[0] = __ldg(p.row_scale + g.opix); return; }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (t < mask_taps) {
+          const int r = t / p.mask_S, s2 = t - r * p.mask_S;
+          const int ih = g.oh * p.mask_stride - p.mask_pad + r * p.mask_dil;
+          const int iw = g.ow * p.mask_stride - p.mask_pad + s2 * p.mask_dil;
+          if (ih >= 0 && ih < p.mask_H && iw >= 0 && iw < p.mask_W)
+            mv[t] = __ldg(p.mask_in + ((long long)g.n * p.mask_H + ih) * p.mask_W + iw);
+        }
+      }
+    };
+    RowGeo geo = geometry(blockIdx.x < total_tiles ? blockIdx.x : 0);
+    float mv[9];
+    load_mask(geo, mv);
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int kt = tile % p.tiles_k, mt = tile / p.tiles_k;
-      const int wi = mt % p.tiles_w, hi = (mt / p.tiles_w) % p.tiles_h, ni = mt / (p.tiles_w * p.tiles_h);
-      const int bn = row / brick, rem = row - bn * brick;
-      const int bh = rem / p.BW, bw = rem - bh * p.BW;
-      const int n = ni * p.BNI + bn, oh = hi * p.BH + bh, ow = wi * p.BW + bw;
-      const int sh = oh * p.out_stride_sp + p.out_off_h, sw = ow * p.out_stride_sp + p.out_off_w;
-      const bool valid = (bn < p.BNI) && (n < p.N) && (oh < p.Ho) && (ow < p.Wo) && (sh < p.out_H) && (sw < p.out_W);
+      const int kt = geo.kt, wi = geo.wi, hi = geo.hi, ni = geo.ni;
+      const bool valid = geo.valid;
+      const long long opix = geo.opix;
       float scale = 1.f, mo = 1.f;
-      long long opix = 0;
       if (valid) {
-        const long long pix = ((long long)n * p.Ho + oh) * p.Wo + ow;
-        opix = ((long long)n * p.out_H + sh) * p.out_W + sw;
         if (p.scale_mode == 1) {
           float cnt = 0.f;
-          for (int r = 0; r < p.mask_R; ++r) {
-            const int ih = oh * p.mask_stride - p.mask_pad + r * p.mask_dil;
-            if (ih < 0 || ih >= p.mask_H) continue;
-            for (int s = 0; s < p.mask_S; ++s) {
-              const int iw = ow * p.mask_stride - p.mask_pad + s * p.mask_dil;
-              if (iw < 0 || iw >= p.mask_W) continue;
-              cnt += __ldg(p.mask_in + ((long long)n * p.mask_H + ih) * p.mask_W + iw);
+          if (prefetch_mask) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) cnt += mv[t];            // same order as the loop below (row-major taps)
+          } else {
+            for (int r = 0; r < p.mask_R; ++r) {
+              const int ih = geo.oh * p.mask_stride - p.mask_pad + r * p.mask_dil;
+              if (ih < 0 || ih >= p.mask_H) continue;
+              for (int s2 = 0; s2 < p.mask_S; ++s2) {
+                const int iw = geo.ow * p.mask_stride - p.mask_pad + s2 * p.mask_dil;
+                if (iw < 0 || iw >= p.mask_W) continue;
+                cnt += __ldg(p.mask_in + ((long long)geo.n * p.mask_H + ih) * p.mask_W + iw);
+              }
             }
           }
-          scale = pconv_ratio((float)(p.mask_R * p.mask_S), cnt);
+          scale = pconv_ratio((float)mask_taps, cnt);
           mo = fminf(fmaxf(cnt, 0.f), 1.f);
           if (kt == 0 && half == 0) {
-            if (p.mask_out) p.mask_out[pix] = mo;
-            if (p.ratio_out) p.ratio_out[pix] = scale;
+            if (p.mask_out) p.mask_out[geo.pix] = mo;
+            if (p.ratio_out) p.ratio_out[geo.pix] = scale;
           }
         } else if (p.scale_mode == 2) {
-          scale = __ldg(p.row_scale + opix);
+          scale = mv[0];
         }
+      }
+      {                                                           // next tile: geometry now, mask loads in flight
+        const int nt = tile + (int)gridDim.x;
+        geo = geometry(nt < total_tiles ? nt : tile);
+        if (nt < total_tiles) load_mask(geo, mv);
       }
       mbar_wait(&bars->tfull[acc], acc_phase);
       tc_fence_after();
@@ -488,29 +538,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const float sc = valid ? scale : 0.f;
         const uint64_t sc2 = pack2(sc, sc);
         const bool unit = p.scale_mode == 0 && valid;
-        uint32_t va[32], vb[32];
-        tmem_ld16(taddr + half * 32, va);
-        tmem_ld16(taddr + half * 32 + 16, va + 16);
-        for (int g = 0; g < groups; ++g) {
-          uint32_t* v = (g & 1) ? vb : va;
-          uint32_t* vn = (g & 1) ? va : vb;
-          tmem_ld_wait();
-          if (g + 1 < groups) {
-            tmem_ld16(taddr + (g + 1) * 64 + half * 32, vn);
-            tmem_ld16(taddr + (g + 1) * 64 + half * 32 + 16, vn + 16);
-          }
-          uint8_t* sbuf = sset + (size_t)g * kABytes;
+        const uint32_t sset_a = smem_u32(sset);
+        const uint32_t row_off = (uint32_t)row * 128u;
+        const uint32_t swz = (uint32_t)(row & 7);
+        // convert one 32-column half-group held in registers and store it to its swizzled staging rows (explicit
+        // shared-space stores; the register arrays are indexed statically -- round 1's `(g & 1) ? vb : va` selection
+        // cost one SEL per value and group, 20 % of the kernel's instructions in ncu)
+        auto convert_store = [&](const uint32_t (&v)[32], int g) {
+          const uint32_t sbuf = sset_a + (uint32_t)g * kABytes + row_off;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j2 = 0; j2 < 4; ++j2) {
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float a = __uint_as_float(v[j * 8 + 2 * e]), b = __uint_as_float(v[j * 8 + 2 * e + 1]);
+              float a = __uint_as_float(v[j2 * 8 + 2 * e]), b = __uint_as_float(v[j2 * 8 + 2 * e + 1]);
               if (!unit) unpack2(mul2(pack2(a, b), sc2), a, b);
               w[e] = f32x2_to_bf16x2(a, b);
             }
-            const int chunk = half * 4 + j;
-            *reinterpret_cast<uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            sts128(sbuf + ((((uint32_t)(half * 4 + j2)) ^ swz) << 4), w[0], w[1], w[2], w[3]);
+          }
+        };
+        auto load_group = [&](uint32_t (&v)[32], int g) {
+          tmem_ld16(taddr + g * 64 + half * 32, v);
+          tmem_ld16(taddr + g * 64 + half * 32 + 16, v + 16);
+        };
+        // software-pipelined TMEM reads, fully unrolled over the (at most four) 64-column groups: the loads of
+        // group g + 1 are in flight while group g is converted
+        uint32_t va[32], vb[32];
+        load_group(va, 0);
+#pragma unroll
+        for (int g2 = 0; g2 < 4; g2 += 2) {
+          if (g2 < groups) {
+            tmem_ld_wait();
+            if (g2 + 1 < groups) load_group(vb, g2 + 1);
+            convert_store(va, g2);
+          }
+          if (g2 + 1 < groups) {
+            tmem_ld_wait();
+            if (g2 + 2 < groups) load_group(va, g2 + 2);
+            convert_store(vb, g2 + 1);
           }
         }
         tc_fence_before();                        // accumulator fully read: hand TMEM back to the MMA warp
@@ -542,11 +608,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < 2; ++k) {
             const int g = ghalf + 2 * k;
             if (g < groups) {
-              const uint8_t* sbuf = sset + (size_t)g * kABytes + off;
+              const uint32_t sbuf = sset_a + (uint32_t)g * kABytes + off;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 if (rsub + 16 * i < nrows) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(sbuf + i * 2048);
+                  const uint4 u = lds128(sbuf + i * 2048);
                   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {

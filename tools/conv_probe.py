@@ -21,6 +21,11 @@ SHAPES = {
     "regressor": (16, 16, 2048, 272, 3, 3, 1, 1, 1, False),
     "stem_rgb": (256, 256, 3, 64, 7, 7, 2, 3, 1, False),
     "pc_3x3_64": (64, 64, 64, 64, 3, 3, 1, 1, 1, True),
+    "pc_1x1_64_256": (64, 64, 64, 256, 1, 1, 1, 0, 1, True),
+    "pc_1x1_256_64": (64, 64, 256, 64, 1, 1, 1, 0, 1, True),
+    "pc_3x3_128": (32, 32, 128, 128, 3, 3, 1, 1, 1, True),
+    "pc_1x1_128_512": (32, 32, 128, 512, 1, 1, 1, 0, 1, True),
+    "pc_stem": (256, 256, 1, 64, 7, 7, 2, 3, 1, True),
 }
 
 
