@@ -537,7 +537,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // of plain 3x3 layers whose output is not a multiple of the brick, e.g. every 257x257 configuration).
         const float sc = valid ? scale : 0.f;
         const uint64_t sc2 = pack2(sc, sc);
-        const bool unit = p.scale_mode == 0 && valid;
         const uint32_t sset_a = smem_u32(sset);
         const uint32_t row_off = (uint32_t)row * 128u;
         const uint32_t swz = (uint32_t)(row & 7);
@@ -551,8 +550,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float a = __uint_as_float(v[j2 * 8 + 2 * e]), b = __uint_as_float(v[j2 * 8 + 2 * e + 1]);
-              if (!unit) unpack2(mul2(pack2(a, b), sc2), a, b);
+              // always multiply (scale 1 when the layer has no row scale): a conditional in-place multiply costs two
+              // register moves per pair, more than the FMUL2 it saves
+              float a, b;
+              unpack2(mul2(pack2(__uint_as_float(v[j2 * 8 + 2 * e]), __uint_as_float(v[j2 * 8 + 2 * e + 1])), sc2), a, b);
               w[e] = f32x2_to_bf16x2(a, b);
             }
             sts128(sbuf + ((((uint32_t)(half * 4 + j2)) ^ swz) << 4), w[0], w[1], w[2], w[3]);
@@ -611,15 +612,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const uint32_t sbuf = sset_a + (uint32_t)g * kABytes + off;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                if (rsub + 16 * i < nrows) {
-                  const uint4 u = lds128(sbuf + i * 2048);
-                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                // rows past the tile contribute zeros: the accumulation itself is unconditional (a guarded update
+                // compiled to a branch per row plus sixteen register moves)
+                uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                if (rsub + 16 * i < nrows) u = lds128(sbuf + i * 2048);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const uint64_t t = bf16x2_to_f32x2(w[e]);
-                    st_sum[k][e] = add2(st_sum[k][e], t);
-                    st_sq[k][e] = fma2(t, t, st_sq[k][e]);
-                  }
+                for (int e = 0; e < 4; ++e) {
+                  const uint64_t t = bf16x2_to_f32x2(w[e]);
+                  st_sum[k][e] = add2(st_sum[k][e], t);
+                  st_sq[k][e] = fma2(t, t, st_sq[k][e]);
                 }
               }
             }
