@@ -4,12 +4,17 @@
 // the unfused pieces kept for API compatibility, and the root-relative masked loss
 // (depth_train.py:397-405).
 //
-// Forward: one CTA per sample.  Every thread owns one logit channel (d, j) over a subset of the
-// pixels and keeps an online-softmax state (max, sum e, sum e*gx, sum e*gy); states are merged per
-// channel, then over d for every joint.  The logits are read exactly once, coalesced in either
-// layout (NHWC: consecutive threads = consecutive channels of a pixel; NCHW: consecutive lanes =
-// consecutive pixels of a channel plane).
+// Forward: one thread-block CLUSTER of kHeadSplit CTAs per sample (64 samples alone leave 84 of the 148 SMs idle),
+// every CTA owns a contiguous slice of the pixels.  Every thread owns one logit channel (d, j) over a subset of its
+// CTA's pixels and keeps an online-softmax state (max, sum e, sum e*gx, sum e*gy); states are merged per channel
+// inside the CTA, then across the cluster through distributed shared memory by the cluster's first CTA, then over d
+// for every joint.  The logits are read exactly once, coalesced in either layout (NHWC: consecutive threads =
+// consecutive channels of a pixel; NCHW: consecutive lanes = consecutive pixels of a channel plane).
+#include <cooperative_groups.h>
+
 #include "b2_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -19,6 +24,8 @@ __device__ __forceinline__ float grid_coord(int i, int n) {
   float step = 2.f / (float)(n - 1);
   return (i < n / 2) ? (float)i * step : 2.f - (float)(n - 1 - i) * step;
 }
+
+constexpr int kHeadSplit = 8;     // CTAs per sample (portable cluster size)
 
 struct St {
   float m, s, a, b;   // running max, sum e, sum e*gx(w), sum e*gy(h)
@@ -54,8 +61,12 @@ __global__ void __launch_bounds__(1024) head_fwd_kernel(const T* __restrict__ lo
   St* ch = reinterpret_cast<St*>(smem4);
   float* jm = reinterpret_cast<float*>(ch + CH);
   float* js = jm + J;
-  const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int n = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
   const T* base = logits + (long long)n * CH * HW;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), nsplit = (int)cluster.num_blocks();
+  const int per_cta = (HW + nsplit - 1) / nsplit;
+  const int p_lo = min(HW, rank * per_cta), p_hi = min(HW, p_lo + per_cta);      // this CTA's pixels
 
   if (LAYOUT == 0) {
     St* part = reinterpret_cast<St*>(js + J + ((4 - ((2 * J) & 3)) & 3));
@@ -67,7 +78,7 @@ __global__ void __launch_bounds__(1024) head_fwd_kernel(const T* __restrict__ lo
       bool act = c < CH && pl < PL;
       t.m = -INFINITY; t.s = t.a = t.b = 0.f;
       if (act) {
-        for (int p = pl; p < HW; p += PL) {
+        for (int p = p_lo + pl; p < p_hi; p += PL) {
           float x = to_f(base[(long long)p * CH + c]);
           st_push(t, x, grid_coord(p % W, W), grid_coord(p / W, H));
         }
@@ -88,7 +99,7 @@ __global__ void __launch_bounds__(1024) head_fwd_kernel(const T* __restrict__ lo
     for (int c = warp; c < CH; c += nw) {
       St t = {-INFINITY, 0.f, 0.f, 0.f};
       const T* plane = base + (long long)c * HW;
-      for (int p = lane; p < HW; p += 32) st_push(t, to_f(plane[p]), grid_coord(p % W, W), grid_coord(p / W, H));
+      for (int p = p_lo + lane; p < p_hi; p += 32) st_push(t, to_f(plane[p]), grid_coord(p % W, W), grid_coord(p / W, H));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         St q;
@@ -101,8 +112,17 @@ __global__ void __launch_bounds__(1024) head_fwd_kernel(const T* __restrict__ lo
       if (lane == 0) ch[c] = t;
     }
   }
+  // merge the per-CTA channel states across the cluster (rank 0 reads its peers' shared memory)
+  cluster.sync();
+  if (rank == 0) {
+    for (int c = tid; c < CH; c += nt) {
+      St t = ch[c];
+      for (int r = 1; r < nsplit; ++r) t = st_merge(t, cluster.map_shared_rank(ch, r)[c]);
+      ch[c] = t;
+    }
+  }
   __syncthreads();
-  for (int j = tid; j < J; j += nt) {
+  for (int j = tid; rank == 0 && j < J; j += nt) {
     St t = ch[j];
     float m = t.m;
     for (int d = 1; d < D; ++d) m = fmaxf(m, ch[d * J + j].m);
@@ -125,17 +145,21 @@ __global__ void __launch_bounds__(1024) head_fwd_kernel(const T* __restrict__ lo
     jm[j] = m;
     js[j] = inv;
   }
+  cluster.sync();            // rank 0 is done with its peers' shared memory; jm / js are final
   if (WRITE_HEAT) {
-    __syncthreads();
-    const long long total = (long long)CH * HW;
+    const float* rjm = cluster.map_shared_rank(jm, 0);
+    const float* rjs = cluster.map_shared_rank(js, 0);
+    const long long total = (long long)CH * (p_hi - p_lo);
     for (long long i = tid; i < total; i += nt) {
       int c, p;
-      if (LAYOUT == 0) { p = (int)(i / CH); c = (int)(i - (long long)p * CH); }
-      else { c = (int)(i / HW); p = (int)(i - (long long)c * HW); }
+      if (LAYOUT == 0) { p = p_lo + (int)(i / CH); c = (int)(i % CH); }
+      else { c = (int)(i / (p_hi - p_lo)); p = p_lo + (int)(i % (p_hi - p_lo)); }
       int j = c % J, d = c / J;
-      float e = __expf(to_f(base[i]) - jm[j]) * js[j];
+      const long long src = (LAYOUT == 0) ? (long long)p * CH + c : (long long)c * HW + p;
+      float e = __expf(to_f(base[src]) - rjm[j]) * rjs[j];
       heat[(((long long)n * J + j) * HW + p) * D + d] = e;
     }
+    cluster.sync();          // peers read rank 0's jm / js until here
   }
 }
 
@@ -162,6 +186,47 @@ __global__ void head_bwd_kernel(const T* __restrict__ logits, const float* __res
     float ug = (u[0] * grid_coord(w, W) + u[1] * grid_coord(h, H) + u[2] * grid_coord(d, D)) * range;
     float uc = u[0] * cc[0] + u[1] * cc[1] + u[2] * cc[2];
     dlogits[i] = from_f<T>(prob * (ug - uc));
+  }
+}
+
+// NHWC with CH % 8 == 0: one thread = 8 consecutive channels of one pixel (16-byte bf16 / 2 x 16-byte fp32 accesses,
+// 32-bit index arithmetic)
+template <typename T>
+__global__ void head_bwd_vec_kernel(const T* __restrict__ logits, const float* __restrict__ dcoords,
+                                    const float* __restrict__ coords, const float* __restrict__ vmax,
+                                    const float* __restrict__ vsum, int N, int J, int D, int H, int W, float range,
+                                    T* __restrict__ dlogits) {
+  const int CH = D * J, HW = H * W, CV = CH >> 3;
+  const int total = N * HW * CV;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % CV, np = i / CV, p = np % HW, n = np / HW;
+    const int h = p / W, w = p - h * W;
+    const float gx = grid_coord(w, W), gy = grid_coord(h, H);
+    const long long off = (long long)np * CH + v * 8;
+    float x[8], o[8];
+    if (sizeof(T) == 2) {
+      load8(reinterpret_cast<const bf16*>(logits) + off, x);
+    } else {
+      const float4 a = load4(reinterpret_cast<const float*>(logits) + off), b = load4(reinterpret_cast<const float*>(logits) + off + 4);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = v * 8 + e, d = c / J, j = c - d * J;
+      const int nj = n * J + j;
+      const float* u = dcoords + (long long)nj * 3;
+      const float* cc = coords + (long long)nj * 3;
+      const float prob = __expf(x[e] - vmax[nj]) / vsum[nj];
+      const float ug = (u[0] * gx + u[1] * gy + u[2] * grid_coord(d, D)) * range;
+      const float uc = u[0] * cc[0] + u[1] * cc[1] + u[2] * cc[2];
+      o[e] = prob * (ug - uc);
+    }
+    if (sizeof(T) == 2) {
+      store8(reinterpret_cast<bf16*>(dlogits) + off, o);
+    } else {
+      store4(reinterpret_cast<float*>(dlogits) + off, make_float4(o[0], o[1], o[2], o[3]));
+      store4(reinterpret_cast<float*>(dlogits) + off + 4, make_float4(o[4], o[5], o[6], o[7]));
+    }
   }
 }
 
@@ -291,7 +356,20 @@ int launch_head_fwd(const void* logits, int N, int J, int D, int H, int W, float
   B2_REQUIRE(sh <= 200 * 1024, B2_E_UNSUPPORTED, "head_fwd: D*J=%d too large", CH);
   auto kern = heat ? head_fwd_kernel<T, LAYOUT, true> : head_fwd_kernel<T, LAYOUT, false>;
   if (sh > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-  kern<<<N, nt, sh, st>>>((const T*)logits, J, D, H, W, range, coords, vmax, vsum, heat);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kHeadSplit, N, 1);
+  cfg.blockDim = dim3(nt, 1, 1);
+  cfg.dynamicSmemBytes = sh;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kHeadSplit;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, (const T*)logits, J, D, H, W, range, coords, vmax, vsum, heat);
+  B2_REQUIRE(le == cudaSuccess, B2_E_LAUNCH, "head_fwd: launch failed: %s", cudaGetErrorString(le));
   B2_LAUNCH_CHECK("head_fwd");
   return B2_OK;
 }
@@ -338,6 +416,13 @@ static int launch_head_bwd(const void* logits, const float* dcoords, const float
                            const float* vsum, int N, int J, int D, int H, int W, float range, void* dlogits,
                            cudaStream_t st) {
   long long total = (long long)N * D * J * H * W;
+  if (LAYOUT == 0 && (D * J) % 8 == 0 && total < (1LL << 31) &&
+      (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0) {
+    head_bwd_vec_kernel<T><<<ew_grid(total / 8), 256, 0, st>>>((const T*)logits, dcoords, coords, vmax, vsum, N, J, D, H, W,
+                                                              range, (T*)dlogits);
+    B2_LAUNCH_CHECK("head_bwd");
+    return B2_OK;
+  }
   head_bwd_kernel<T, LAYOUT><<<ew_grid(total), 256, 0, st>>>((const T*)logits, dcoords, coords, vmax, vsum, N, J, D,
                                                            H, W, range, (T*)dlogits);
   B2_LAUNCH_CHECK("head_bwd");

@@ -51,7 +51,7 @@ print("per step: span %.3f ms, some kernel running %.3f ms (%.1f%%), sum of kern
       % (span / 1e3, busy / a.steps / 1e3, 100 * busy / (t1 - t0), total / a.steps / 1e3, total / busy))
 agg = collections.defaultdict(lambda: [0, 0.0])
 for s, e, n, _ in ks:
-    k = n.split("(")[0].replace("void ", "").replace("(anonymous namespace)::", "")[:60]
+    k = n.replace("void ", "").replace("(anonymous namespace)::", "").split("(")[0][:60]
     agg[k][0] += 1
     agg[k][1] += e - s
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:18]:
