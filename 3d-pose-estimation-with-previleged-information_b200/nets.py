@@ -241,7 +241,8 @@ class ResNet(nn.Module):
         x = ops.to_nhwc(inp, self.compute_dtype)
         partial = isinstance(conv, PartialConv)
         veil = ops.veil_from_depth(x) if partial else None          # partial_depthnet.py:215
-        x, veil = conv_bn(x, veil, conv, bn, relu=True)
+        # veil = (x != 0), so x * veil == x exactly: the stem reads its input as already masked
+        x, veil = conv_bn(x, veil, conv, bn, relu=True, premasked=True)
         return ops.MaxPoolFn.apply(x, veil)                          # x and veil pooled together (:219-220)
 
     def forward(self, x, y=None):
