@@ -111,7 +111,7 @@ class BatchNorm2d(nn.BatchNorm2d):
 
 
 def conv_bn(x, veil, conv, bn, relu, residual=None, mask_output=False, premasked=False, dx_holder=None,
-            res_holder=None):
+            res_holder=None, park_holder=None):
     """conv -> bn (+residual) (+relu) (*veil) on NHWC tensors; returns (z, veil_out)."""
     partial = isinstance(conv, PartialConv)
     training = bn.training
@@ -125,6 +125,7 @@ def conv_bn(x, veil, conv, bn, relu, residual=None, mask_output=False, premasked
     if conv._grad_sink is not None and bn._grad_sinks is not None and torch.is_grad_enabled():
         sinks = (conv._grad_sink,) + bn._grad_sinks
     z, vout = ops.ConvBNFn.apply(x, veil if partial else None, conv.weight, conv.shadow(x.dtype), bn.weight,
-                                 bn.bias, bn.running_mean, bn.running_var, residual, cfg, sinks, dx_holder, res_holder)
+                                 bn.bias, bn.running_mean, bn.running_var, residual, cfg, sinks, dx_holder, res_holder,
+                                 park_holder)
     bn.tick()
     return z, (vout if partial else veil)

@@ -39,13 +39,18 @@ class _Block(nn.Module):
         self.skip_relu = skip_relu
 
     def _holder(self, x):
-        """Shared dict that lets the block's first conv+BN node absorb the identity shortcut's gradient
-        (see ops.ConvBNFn); only when the shortcut is the block input itself."""
-        return {} if (self.downsample is None and torch.is_grad_enabled() and x.requires_grad) else None
+        """Shared dict that lets the block's first conv+BN node absorb the shortcut's gradient with a TMA reduce-add
+        instead of a separate add kernel (see ops.ConvBNFn): the identity shortcut's gradient is parked by the block's
+        LAST node, a down-sampling shortcut's by the shortcut node itself."""
+        if not (torch.is_grad_enabled() and x.requires_grad):
+            return None
+        return {} if self.downsample is None else {"open": True}
 
-    def _residual(self, x):
-        """Shortcut branch.  A down-sampling shortcut (1x1 conv + BN) runs on its own stream beside the block's main
-        path (forward here, backward through autograd's stream affinity); `_join` is called before it is consumed."""
+    def _residual(self, x, holder=None):
+        """Shortcut branch, called right AFTER the block's first conv+BN node was created (autograd runs later-created
+        nodes first, so the shortcut's backward precedes the first node's and can hand it its dx through `holder`).
+        A down-sampling shortcut (1x1 conv + BN) runs on its own stream beside the block's main path (forward here,
+        backward through autograd's stream affinity); `_join` is called before it is consumed."""
         self._side = None
         if self.downsample is None:
             return x
@@ -53,10 +58,10 @@ class _Block(nn.Module):
             cur, side = torch.cuda.current_stream(x.device), ops.shortcut_stream(x.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                res, _ = conv_bn(x, None, self.downsample[0], self.downsample[1], relu=False)
+                res, _ = conv_bn(x, None, self.downsample[0], self.downsample[1], relu=False, park_holder=holder)
             self._side = (cur, side)
             return res
-        res, _ = conv_bn(x, None, self.downsample[0], self.downsample[1], relu=False)
+        res, _ = conv_bn(x, None, self.downsample[0], self.downsample[1], relu=False, park_holder=holder)
         return res
 
     def _join(self, res):
@@ -83,10 +88,11 @@ class BasicBlock(_Block):
         self.stride = stride
 
     def forward_nhwc(self, x, veil):
-        res, h = self._residual(x), self._holder(x)
+        h = self._holder(x)
         out, veil = conv_bn(x, veil, self.conv1, self.bn1, relu=True, mask_output=True, dx_holder=h)
+        res = self._residual(x, h)
         out, veil = conv_bn(out, veil, self.conv2, self.bn2, relu=not self.skip_relu, residual=self._join(res),
-                            premasked=True, res_holder=h)
+                            premasked=True, res_holder=h if self.downsample is None else None)
         return out, veil
 
 
@@ -107,11 +113,12 @@ class Bottleneck(_Block):
         self.stride = stride
 
     def forward_nhwc(self, x, veil):
-        res, h = self._residual(x), self._holder(x)
+        h = self._holder(x)
         out, veil = conv_bn(x, veil, self.conv1, self.bn1, relu=True, mask_output=True, dx_holder=h)
+        res = self._residual(x, h)
         out, veil = conv_bn(out, veil, self.conv2, self.bn2, relu=True, mask_output=True, premasked=True)
         out, veil = conv_bn(out, veil, self.conv3, self.bn3, relu=not self.skip_relu, residual=self._join(res),
-                            premasked=True, res_holder=h)
+                            premasked=True, res_holder=h if self.downsample is None else None)
         return out, veil
 
 

@@ -435,11 +435,14 @@ class ConvBNFn(Function):
 
     @staticmethod
     def forward(ctx, x, mask, weight, shadow, gamma, beta, running_mean, running_var, residual, cfg, sinks=None,
-                dx_holder=None, res_holder=None):
+                dx_holder=None, res_holder=None, park_holder=None):
         # dx_holder / res_holder: a dict shared by the first and the last conv+BN node of a residual
         # block with identity shortcut.  The last node parks the shortcut's gradient there instead of
         # returning it; the first node (whose backward always runs later) folds it into its dx with a
         # TMA reduce-add, so autograd never launches a separate add over the block input's gradient.
+        # park_holder: the same dict handed to the block's down-sampling shortcut node (1x1 conv + BN on the block
+        # input, created right AFTER the first node so that autograd runs its backward before the first node's): it parks
+        # its own dx there, with an event of its stream, instead of returning it.
         stride, pad, dil, partial, premasked, relu, mask_output, training, momentum, eps, force_ffma = cfg
         L.require_cuda(x, mask, weight, gamma)
         x = x.contiguous()
@@ -495,7 +498,7 @@ class ConvBNFn(Function):
         ctx.desc, ctx.relu, ctx.training, ctx.wdtype = desc, relu, training, weight.dtype
         ctx.has_res = residual is not None
         ctx.sinks = sinks
-        ctx.dx_holder, ctx.res_holder = dx_holder, res_holder
+        ctx.dx_holder, ctx.res_holder, ctx.park_holder = dx_holder, res_holder, park_holder
         # z is only needed for the ReLU gate of residual layers; otherwise the gate is recomputed from y
         ctx.save_for_backward(x, mask if partial else None, wk, ratio, y,
                               z if (relu and residual is not None and gate is None) else None,
@@ -543,7 +546,15 @@ class ConvBNFn(Function):
             if dw is not None:
                 dw = dw.to(ctx.wdtype)
         if ctx.needs_input_grad[0]:
-            addend = ctx.dx_holder.pop("dres", None) if ctx.dx_holder is not None else None
+            addend = None
+            if ctx.dx_holder is not None:
+                addend = ctx.dx_holder.pop("dres", None)
+                ev = ctx.dx_holder.pop("ev", None)
+                ctx.dx_holder["open"] = False            # a shortcut node that runs later returns its dx to autograd
+                if ev is not None:                       # parked on the shortcut's stream
+                    cur = torch.cuda.current_stream(dev)
+                    cur.wait_event(ev)
+                    addend.record_stream(cur)
             if ctx.self_masked:                  # x was masked in this node: dgrad scales its rows by the mask
                 desc.flags &= ~L.CONV_X_PREMASKED
             wt = ctx.wt
@@ -561,7 +572,13 @@ class ConvBNFn(Function):
         if dres is not None and ctx.res_holder is not None:
             ctx.res_holder["dres"] = dres          # delivered through the block's first node
             dres = None
-        return dx, None, dw, None, dgamma, dbeta, None, None, dres, None, None, None, None
+        if dx is not None and ctx.park_holder is not None and ctx.park_holder.get("open", False) \
+                and "dres" not in ctx.park_holder:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            ctx.park_holder["dres"], ctx.park_holder["ev"] = dx, ev
+            dx = None
+        return dx, None, dw, None, dgamma, dbeta, None, None, dres, None, None, None, None, None
 
 
 class MaxPoolFn(Function):
