@@ -989,25 +989,26 @@ im2col_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* 
 // (round 1 wrote N*Ho*Wo*152 bf16 = 319 MB to HBM and read it back, twice per step).  The layer then IS a convolution
 // with R = 7, S = 1, C = 64 for the generic kernels: window element j = 4 p + c holds pixel 2ow - 4 + p, channel c, so
 // the filter is laid out as Wk[k][r][j] = W[k][r][s = p - 1][c] (zero for p = 0, p > 7, c >= C).
-__global__ void vw_pad_kernel(const bf16* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ xp, int N,
-                              int H, int W, int C, int Hp, int Wp) {
-  const long long total = (long long)N * Hp * Wp;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int wp = (int)(i % Wp);
-    const long long t = i / Wp;
-    const int hp = (int)(t % Hp), n = (int)(t / Hp);
-    const int h = hp - 3, w = wp - 4;
+__global__ void __launch_bounds__(256) vw_pad_kernel(const bf16* __restrict__ x, const float* __restrict__ mask,
+                                                     bf16* __restrict__ xp, int H, int W, int C, int Hp, int Wp) {
+  // one block = one padded image row (blockIdx.x = n * Hp + hp): no divisions per pixel
+  const int hp = blockIdx.x % Hp, n = blockIdx.x / Hp;
+  const int h = hp - 3;
+  const bool row_ok = h >= 0 && h < H;
+  const long long src_row = ((long long)n * H + h) * W;
+  bf16* dst = xp + (long long)blockIdx.x * Wp * 4;
+  for (int wp = threadIdx.x; wp < Wp; wp += blockDim.x) {
+    const int w = wp - 4;
     uint32_t lo = 0, hi = 0;
-    if (h >= 0 && h < H && w >= 0 && w < W) {
-      const long long ip = ((long long)n * H + h) * W + w;
+    if (row_ok && w >= 0 && w < W) {
+      const long long ip = src_row + w;
       const float m = mask ? mask[ip] : 1.f;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       for (int c = 0; c < C; ++c) v[c] = __bfloat162float(x[ip * C + c]) * m;
       lo = f32x2_to_bf16x2(v[0], v[1]);
       hi = f32x2_to_bf16x2(v[2], v[3]);
     }
-    *reinterpret_cast<uint2*>(xp + i * 4) = make_uint2(lo, hi);
+    *reinterpret_cast<uint2*>(dst + (long long)wp * 4) = make_uint2(lo, hi);
   }
 }
 // Wk[k][r][4 p + c] = W[k][r][p - 1][c]
@@ -1283,10 +1284,7 @@ inline size_t vw_view_bytes(const B2ConvDesc* d) { return (size_t)d->N * vw_hp(d
 inline int stem_kpad(const B2ConvDesc* d) { return (d->R * d->S * d->C + 7) / 8 * 8; }
 
 int launch_vw_pad(const B2ConvDesc* d, const void* x, const float* mask, bf16* xp, cudaStream_t st) {
-  const long long total = (long long)d->N * vw_hp(d) * vw_wp(d);
-  long long want = (total + 255) / 256, cap = (long long)b2_num_sms() * 16;
-  vw_pad_kernel<<<(int)(want > cap ? cap : want), 256, 0, st>>>((const bf16*)x, mask, xp, d->N, d->H, d->W, d->C, vw_hp(d),
-                                                              vw_wp(d));
+  vw_pad_kernel<<<d->N * vw_hp(d), 256, 0, st>>>((const bf16*)x, mask, xp, d->H, d->W, d->C, vw_hp(d), vw_wp(d));
   B2_LAUNCH_CHECK("vw_pad");
   return B2_OK;
 }

@@ -179,6 +179,45 @@ __global__ void mask_update_kernel(const float* __restrict__ mask_in, float* __r
   }
 }
 
+// Box-window version for the dense window of the stems (dil == 1): one block = kMuRows output rows of one image.  The
+// input rows are staged in shared memory, summed horizontally once per (input row, output column) and then vertically,
+// instead of R*S global loads per output.  Sums of {0, 1} values are exact in any order, so the results are bit-identical.
+constexpr int kMuRows = 8;
+__global__ void __launch_bounds__(256) mask_update_box_kernel(const float* __restrict__ mask_in, float* __restrict__ mask_out,
+                                                              float* __restrict__ ratio_out, int H, int W, int R, int S,
+                                                              int stride, int pad, int Ho, int Wo) {
+  extern __shared__ float mu_sm[];
+  const int in_rows = (kMuRows - 1) * stride + R;
+  float* rows = mu_sm;                       // [in_rows][W]
+  float* hsum = mu_sm + (size_t)in_rows * W; // [in_rows][Wo]
+  const int n = blockIdx.y, oh0 = blockIdx.x * kMuRows, ih0 = oh0 * stride - pad;
+  const float* src = mask_in + (long long)n * H * W;
+  for (int i = threadIdx.x; i < in_rows * W; i += blockDim.x) {
+    const int r = i / W, w = i - r * W, ih = ih0 + r;
+    rows[i] = (ih >= 0 && ih < H) ? src[(long long)ih * W + w] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < in_rows * Wo; i += blockDim.x) {
+    const int r = i / Wo, ow = i - r * Wo, iw0 = ow * stride - pad;
+    float a = 0.f;
+    for (int s2 = 0; s2 < S; ++s2) {
+      const int iw = iw0 + s2;
+      if (iw >= 0 && iw < W) a += rows[r * W + iw];
+    }
+    hsum[i] = a;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMuRows * Wo; i += blockDim.x) {
+    const int orow = i / Wo, ow = i - orow * Wo, oh = oh0 + orow;
+    if (oh >= Ho) continue;
+    float cnt = 0.f;
+    for (int r = 0; r < R; ++r) cnt += hsum[(orow * stride + r) * Wo + ow];
+    const long long m = ((long long)n * Ho + oh) * Wo + ow;
+    if (mask_out) mask_out[m] = fminf(fmaxf(cnt, 0.f), 1.f);
+    if (ratio_out) ratio_out[m] = pconv_ratio((float)(R * S), cnt);
+  }
+}
+
 // ---------------------------------------------------------------- unprojection
 // Vector path (W % 4 == 0, fewer than 2^30 vectors): 32-bit index arithmetic (the 64-bit divisions of the generic kernel below cap it at 58 % of the HBM
 // rate) and two independent 16-byte loads in flight per thread.
@@ -432,6 +471,15 @@ extern "C" int b2_pconv_mask_update(const B2ConvDesc* d, const float* mask_in, f
                                     void* stream) {
   B2_REQUIRE(d && mask_in && (mask_out || ratio_out), B2_E_BADARG, "mask_update: bad argument");
   long long total = (long long)d->N * d->Ho * d->Wo;
+  const size_t box_sh = ((size_t)((kMuRows - 1) * d->stride + d->R) * (d->W + d->Wo)) * sizeof(float);
+  if (d->dil == 1 && d->R * d->S >= 25 && box_sh <= 160 * 1024) {
+    if (box_sh > 48 * 1024)
+      cudaFuncSetAttribute(mask_update_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_sh);
+    mask_update_box_kernel<<<dim3((d->Ho + kMuRows - 1) / kMuRows, d->N), 256, box_sh, (cudaStream_t)stream>>>(
+        mask_in, mask_out, ratio_out, d->H, d->W, d->R, d->S, d->stride, d->pad, d->Ho, d->Wo);
+    B2_LAUNCH_CHECK("mask_update");
+    return B2_OK;
+  }
   mask_update_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       mask_in, mask_out, ratio_out, d->N, d->H, d->W, d->R, d->S, d->stride, d->pad, d->dil, d->Ho, d->Wo);
   B2_LAUNCH_CHECK("mask_update");
