@@ -1,4 +1,5 @@
 #!/bin/bash
+# bench.py at N GPUs under the gradient-exchange variants (see profiles/r02_ddp_overlap.md)
 N=${1:-2}
 run() {
   tag=$1; shift
@@ -14,5 +15,6 @@ except Exception as e:
 PY
 }
 run default
+run overlap_sms8 B2POSE_DDP_OVERLAP=1 B2POSE_COMM_SMS=8
+run overlap_sms0 B2POSE_DDP_OVERLAP=1 B2POSE_COMM_SMS=0
 run fp32_exchange B2POSE_DDP_BF16=0
-run overlap_bf16 B2POSE_DDP_OVERLAP=1
