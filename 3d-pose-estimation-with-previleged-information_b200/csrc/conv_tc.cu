@@ -1600,7 +1600,13 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   const long long bricks = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
   const long long base_items = (long long)p.tgroups * p.ctiles * p.ktiles;
   // enough pixel splits to fill the machine ~2x, but at least 8 bricks (512 pixels) per item
-  long long want = (2LL * b2_num_sms() + base_items - 1) / base_items;
+  // pixel splits: every split ends in 128 x T x BNc fp32 reductions into dW, which cost as much as ~30 pipeline
+  // stages, and the kernel runs on the side stream beside the BatchNorm / dgrad chain.  Measured in the step
+  // (B2POSE_WGRAD_WAVES = 1 / 2 / 3 / 12): 14.74 / 14.85 / 15.1 / 14.65 ms -- one wave of work items for the 1x1 layers,
+  // two for the multi-tap layers (whose few (tap group, tile) items need the splits for parallelism) = 12, the default
+  static const int env_waves = getenv("B2POSE_WGRAD_WAVES") ? atoi(getenv("B2POSE_WGRAD_WAVES")) : 12;
+  const int waves = env_waves == 12 ? (taps == 1 ? 1 : 2) : env_waves;
+  long long want = ((long long)waves * b2_num_sms() + base_items - 1) / base_items;
   long long max_splits = (bricks + 7) / 8;
   if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
