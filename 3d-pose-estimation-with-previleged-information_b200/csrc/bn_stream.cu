@@ -425,6 +425,8 @@ inline size_t smem_bytes(int nin, bool reduce, bool bits = false) {
 }
 
 inline int stream_grid(long long total_elems, int blocks_per_sm, bool slots) {
+  static const int env_bps = getenv("B2POSE_BNS_BPS") ? atoi(getenv("B2POSE_BNS_BPS")) : 0;      // tuning override
+  if (env_bps > 0) blocks_per_sm = env_bps;
   long long chunks = (total_elems * 2 + kChunkBytes - 1) / kChunkBytes;
   long long g = (long long)b2_num_sms() * blocks_per_sm;
   if (slots && g > B2_BN_PARTS) g = B2_BN_PARTS;

@@ -291,8 +291,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* staging = bres + (p.b_resident ? (size_t)p.kblocks * b_bytes : 0);
   PipeBars* bars = reinterpret_cast<PipeBars*>(staging + (p.tma_store ? p.n_staging * kABytes : 0));
   float* s_stats = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~(uintptr_t)15);
-  if (p.bn_sums)      // [8 epilogue warps][2*K]: warp-private partials, no shared atomics
-    for (int i = threadIdx.x; i < 16 * p.K; i += kConvThreads) s_stats[i] = 0.f;
+  if (p.bn_sums)      // [8 epilogue warps][2*BN]: warp-private partials, no shared atomics
+    for (int i = threadIdx.x; i < 16 * p.BN; i += kConvThreads) s_stats[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
@@ -664,7 +664,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // lanes l and l ^ 16 hold the same channels (rows rsub and rsub ^ 1): combine, then the low half-warp
       // writes this warp's partial; the 8 warp partials are summed in a fixed order below (deterministic)
       const int chunk = ep_tid & 7, ghalf = (ep_tid >> 3) & 1;
-      float* mine = s_stats + (size_t)ew * 2 * p.K;
+      float* mine = s_stats + (size_t)ew * 2 * p.BN;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         float su[8], sq[8];
@@ -682,7 +682,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane < 16 && g < groups) {
           const int ch0 = g * 64 + chunk * 8;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { mine[ch0 + e] = su[e]; mine[p.K + ch0 + e] = sq[e]; }
+          for (int e = 0; e < 8; ++e) { mine[ch0 + e] = su[e]; mine[p.BN + ch0 + e] = sq[e]; }
         }
       }
     }
@@ -691,13 +691,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   if (p.bn_sums) {      // this CTA's slot of partials[B2_BN_PARTS][2K]; the unused slots are zero-filled
+    // With several channel tiles the grid is a multiple of tiles_k, so every tile of this CTA has the same kt =
+    // blockIdx.x % tiles_k and the register accumulators above belong to channels [kt * BN, (kt + 1) * BN).
+    const int kt0 = blockIdx.x % p.tiles_k, c0 = kt0 * p.BN;
     float* slot = p.bn_sums + (p.bn_totals ? (size_t)0 : (size_t)blockIdx.x * 2 * p.K);
-    for (int i = threadIdx.x; i < 2 * p.K; i += kConvThreads) {
+    if (!p.bn_totals && p.tiles_k > 1)
+      for (int i = threadIdx.x; i < 2 * p.K; i += kConvThreads) slot[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * p.BN; i += kConvThreads) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += s_stats[(size_t)w * 2 * p.K + i];
-      if (p.bn_totals) atomicAdd(slot + i, t);
-      else slot[i] = t;
+      for (int w = 0; w < 8; ++w) t += s_stats[(size_t)w * 2 * p.BN + i];
+      const int q = i >= p.BN ? 1 : 0, c = c0 + (i - q * p.BN);
+      if (c < p.K) {
+        if (p.bn_totals) atomicAdd(slot + q * p.K + c, t);
+        else slot[q * p.K + c] = t;
+      }
     }
     if (!p.bn_totals)
       for (int sl = gridDim.x + blockIdx.x; sl < B2_BN_PARTS; sl += gridDim.x)
@@ -1198,11 +1207,16 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   B2_REQUIRE(!a.accumulate || p.tma_store, B2_E_UNSUPPORTED,
              "conv_tc: accumulate needs the TMA-store epilogue (output channels %% 64 == 0, stride 1)");
   // fused statistics for the wide-spatial layers (K <= 256); deeper layers are small and keep the separate pass
-  p.bn_sums = (p.tma_store && a.bn_sums && a.K <= 256 && p.tiles_k == 1 && !no_fused_stats) ? a.bn_sums : nullptr;
+  // fused statistics: the per-thread accumulators live across all tiles of a CTA, so every tile of a CTA must cover
+  // the same channels -- one channel tile, or a grid that is a multiple of tiles_k (below); the deep K > 256 layers
+  // ran a separate pass over their (largest) outputs in round 1
+  const long long total_tiles_h = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_k;
+  const bool multi_ok = p.tiles_k > 1 && a.K % p.BN == 0 && b2_num_sms() >= 2 * p.tiles_k && total_tiles_h >= b2_num_sms();
+  p.bn_sums = (p.tma_store && a.bn_sums && (p.tiles_k == 1 ? a.K <= 256 : multi_ok) && !no_fused_stats) ? a.bn_sums : nullptr;
   p.bn_totals = a.bn_totals;
   if (a.stats_fused) *a.stats_fused = p.bn_sums != nullptr;
   p.n_staging = kStaging;
-  int extra = (p.bn_sums ? 64 * a.K : 0);
+  int extra = (p.bn_sums ? 64 * p.BN : 0);
   // Filter resident in shared memory when one channel tile covers K and the whole filter is small (layer1-type layers,
   // the stems): the ring then carries activation tiles only -- a third to two thirds less L2 -> SM traffic per tile and
   // a deeper ring, which is what bounds these layers (B2POSE_TC_B_RESIDENT=0 disables)
@@ -1250,6 +1264,7 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   }
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_k;
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
+  if (p.bn_sums && p.tiles_k > 1) grid = grid / p.tiles_k * p.tiles_k;      // fixed channel tile per CTA
   cudaError_t le = launch_pdl(conv_tc_kernel, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, mo, p);
   B2_REQUIRE(le == cudaSuccess, B2_E_LAUNCH, "conv_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   B2_LAUNCH_CHECK("conv_tc_kernel");
