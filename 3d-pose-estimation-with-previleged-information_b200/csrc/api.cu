@@ -94,7 +94,7 @@ extern "C" int b2_pconv_dgrad(const B2ConvDesc* d, const void* dy, const float* 
 }
 
 extern "C" size_t b2_pconv_dgrad_filter_bytes(const B2ConvDesc* d) {
-  if (check_desc(d) != B2_OK || !use_tc(d, 1)) return 0;
+  if (check_desc(d) != B2_OK || !use_tc(d, 1) || !conv_tc_dgrad_needs_filter(d)) return 0;
   return (size_t)d->K * d->R * d->S * d->C * 2;
 }
 

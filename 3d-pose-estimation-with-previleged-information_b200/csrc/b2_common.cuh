@@ -193,6 +193,7 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
 int conv_tc_dgrad(const B2ConvDesc* d, const void* dy, const float* ratio, const void* w, const float* mask_in,
                   void* dx, void* workspace, cudaStream_t st);
 int conv_tc_dgrad_filter(const B2ConvDesc* d, const void* w, void* wt, cudaStream_t st);
+bool conv_tc_dgrad_needs_filter(const B2ConvDesc* d);
 int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, const void* dy, const float* ratio,
                   float* dw, void* workspace, cudaStream_t st);
 

@@ -120,7 +120,7 @@ constexpr uint32_t kPoll1 = 1, kPoll2 = 2, kCommit1 = 4, kCommit2 = 8;
 __device__ __forceinline__ void mma4_fused(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint64_t dstep, uint32_t idesc,
                                            uint32_t acc0, uint32_t flags, uint32_t poll1_bar, uint32_t poll1_parity,
                                            uint32_t poll2_bar, uint32_t poll2_parity, uint32_t commit1_bar,
-                                           uint32_t commit2_bar, uint32_t& ready1, uint32_t& ready2) {
+                                           uint32_t commit2_bar, uint32_t& ready1, uint32_t& ready2, uint64_t bstep) {
   asm volatile(
       "{\n\t"
       ".reg .pred pw1, pw2, pe, pa, q1, q2, c1, c2;\n\t"
@@ -136,7 +136,7 @@ __device__ __forceinline__ void mma4_fused(uint32_t tmem_d, uint64_t adesc, uint
       "and.b32 t, %8, 8;\n\tsetp.ne.b32 c2, t, 0;\n\tand.pred c2, c2, pe;\n\t"
       "setp.ne.b32 pa, %7, 0;\n\t"
       "add.s64 a1, %3, %5;\n\tadd.s64 a2, a1, %5;\n\tadd.s64 a3, a2, %5;\n\t"
-      "add.s64 b1, %4, %5;\n\tadd.s64 b2, b1, %5;\n\tadd.s64 b3, b2, %5;\n\t"
+      "add.s64 b1, %4, %15;\n\tadd.s64 b2, b1, %15;\n\tadd.s64 b3, b2, %15;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], %3, %4, %6, pa;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %6, 1;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a2, b2, %6, 1;\n\t"
@@ -147,7 +147,7 @@ __device__ __forceinline__ void mma4_fused(uint32_t tmem_d, uint64_t adesc, uint
       "}"
       : "=r"(ready1), "=r"(ready2)
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "l"(dstep), "r"(idesc), "r"(acc0), "r"(flags), "r"(poll1_bar),
-        "r"(poll1_parity), "r"(poll2_bar), "r"(poll2_parity), "r"(commit1_bar), "r"(commit2_bar)
+        "r"(poll1_parity), "r"(poll2_bar), "r"(poll2_parity), "r"(commit1_bar), "r"(commit2_bar), "l"(bstep)
       : "memory");
 }
 // Producer counterpart of mma4_fused: the single producing thread's serial latency per ring stage (a blocking wait on
@@ -251,6 +251,8 @@ struct FpropParams {
   int cblocks, kblocks;                                // C/64, taps*C/64
   int stages, tmem_cols;
   int b_resident;                                      // the whole filter (kblocks slices of BN rows) stays in shared memory
+  int b_mn;                                            // dgrad straight from the untransposed filter W[k][tap][c]: B tiles are
+                                                       // MN-major atoms [64 k][64 c], taps read in flipped order
   int n_staging;                                       // 16 KB output staging buffers of the TMA-store epilogue (<= kStaging)
   int scale_mode;                                      // 0 none, 1 partial-conv ratio from mask_in, 2 row_scale[]
   int mask_R, mask_S, mask_stride, mask_pad, mask_dil, mask_H, mask_W;   // window geometry for mode 1
@@ -322,11 +324,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (p.b_resident && lane == 0 && !(p.debug & 24)) {
       // the filter is the same for every tile of this CTA (tiles_k == 1): fetch it once
       mbar_expect_tx(&bars->bfull, (uint32_t)p.kblocks * b_bytes);
-      int bcol = 0, cb = 0;
+      int bcol = 0, cb = 0, tap = 0;
       for (int kb = 0; kb < p.kblocks; ++kb) {
-        tma_load_2d(smem_u32(bres + (size_t)kb * b_bytes), &map_b, &bars->bfull, bcol, 0);
+        if (p.b_mn) {
+          for (int a = 0; a < (p.BN >> 6); ++a)
+            tma_load_2d(smem_u32(bres + (size_t)kb * b_bytes + a * 8192), &map_b, &bars->bfull,
+                        (p.R * p.S - 1 - tap) * p.K + a * 64, cb * kBlockK);
+        } else {
+          tma_load_2d(smem_u32(bres + (size_t)kb * b_bytes), &map_b, &bars->bfull, bcol, 0);
+        }
         bcol += kBlockK;
-        if (++cb == p.cblocks) { cb = 0; bcol += p.C - p.cblocks * kBlockK; }
+        if (++cb == p.cblocks) { cb = 0; ++tap; bcol += p.C - p.cblocks * kBlockK; }
       }
     }
     __syncwarp();
@@ -359,9 +367,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           __syncwarp();
         } else {
           const bool has_next = kb + 1 < p.kblocks || more_tiles;
+          const int mn_col = (p.R * p.S - 1 - (r * p.S + s)) * p.K + kt * p.BN;     // b_mn: flipped tap, first atom
           empty_ready = produce_fused((has_next ? 1u : 0u) | stage_flags, smem_u32(&bars->empty[nstage]), nphase ^ 1,
                                       smem_u32(&bars->full[stage]), stage_tx, sa, &map_a, cb * kBlockK,
-                                      iw0 + s * p.dil, ih0 + r * p.dil, n0, sa + kABytes, &map_b, bcol, kt * p.BN);
+                                      iw0 + s * p.dil, ih0 + r * p.dil, n0, sa + kABytes, &map_b,
+                                      p.b_mn ? mn_col : bcol, p.b_mn ? cb * kBlockK : kt * p.BN);
+          if (p.b_mn && !p.b_resident && p.BN > 64) {
+            if (elect_one())
+              for (int a = 1; a < (p.BN >> 6); ++a)
+                tma_load_2d(sa + kABytes + a * 8192, &map_b, &bars->full[stage], mn_col + a * 64, cb * kBlockK);
+            __syncwarp();
+          }
         }
         bcol += kBlockK;
         if (++cb == p.cblocks) {
@@ -378,7 +394,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // The whole warp stays converged (elect.sync inside mma4_fused picks the issuing lane).  Every group of four MMAs
     // polls the barrier the next group needs (`full` of the next ring stage, or the `tempty` of the next tile's
     // accumulator when this is a tile's last k-block), so the blocking waits below normally fall through.
-    const uint32_t idesc = instr_desc(kTileM, p.BN, 0, 0);
+    const uint32_t idesc = instr_desc(kTileM, p.BN, 0, p.b_mn);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
@@ -404,9 +420,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                (last ? kCommit2 : 0u);
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint32_t sb = p.b_resident ? smem_u32(bres + (size_t)kb * b_bytes) : sa + kABytes;
-        mma4_fused(tmem_d, smem_desc(sa, 0, 1024), smem_desc(sb, 0, 1024), 2ull, idesc, (uint32_t)kb, flags,
+        // B: K-major filter slice [BN][64], or (b_mn) BN / 64 MN-major atoms [64 k][64 c] straight from the
+        // untransposed filter: LBO = one 8 KB atom, 16 k-rows per MMA = 2048 B
+        const uint64_t bdesc = p.b_mn ? smem_desc(sb, 8192, 1024) : smem_desc(sb, 0, 1024);
+        mma4_fused(tmem_d, smem_desc(sa, 0, 1024), bdesc, 2ull, idesc, (uint32_t)kb, flags,
                    smem_u32(&bars->full[nstage]), nphase, smem_u32(&bars->tempty[nacc]), nacc_parity,
-                   smem_u32(&bars->empty[stage]), smem_u32(&bars->tfull[acc]), full_ready, acc_ready);
+                   smem_u32(&bars->empty[stage]), smem_u32(&bars->tfull[acc]), full_ready, acc_ready,
+                   p.b_mn ? 128ull : 2ull);
         stage = nstage;
         phase = nphase;
       }
@@ -859,7 +879,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           mma4_fused(tmem_d + (uint32_t)(j * p.BNc), adesc, smem_desc(sa + a_bytes + j * b_bytes, atom_bytes, 1024), 128ull,
                      idesc, (uint32_t)(b - b0), flags, smem_u32(&bars->full[nstage]), nphase,
                      smem_u32(&bars->tempty[nacc]), nacc_parity, smem_u32(&bars->empty[stage]),
-                     smem_u32(&bars->tfull[acc]), q1, q2);
+                     smem_u32(&bars->tfull[acc]), q1, q2, 128ull);
           if (j == 0) { r1 = q1; r2 = q2; }
         }
         full_ready = r1;
@@ -1173,12 +1193,21 @@ struct RunArgs {
   void* out; int out_H, out_W, out_stride_sp, out_off_h, out_off_w;
   int pad_w, use_pad_w;                                        // pad_w is read only when use_pad_w != 0
   int vw_hp, vw_wp;                                            // != 0: `act` is a window-map stem input (make_vw_map)
+  int b_mn;                                                    // filt is the UNtransposed filter [C][R*S*K] (dgrad, see FpropParams)
   int accumulate;                                              // dgrad: reduce-add into `out`
   float* bn_sums; bool* stats_fused; int bn_totals;           // optional fused BatchNorm statistics
   int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
   float* mask_out; float* ratio_out;
   int mask_R, mask_S, mask_stride, mask_pad, mask_dil, mask_H, mask_W;
 };
+
+// output-channel tile: up to 256 wide (measured: narrower tiles only add per-tile overhead, also for the 1x1 layers)
+int choose_bn(int K) {
+  static const int env_cap = getenv("B2POSE_TC_BN_CAP") ? atoi(getenv("B2POSE_TC_BN_CAP")) : 0;
+  const int bn_cap = env_cap > 0 ? env_cap : 256;
+  const int nk = (K + bn_cap - 1) / bn_cap;
+  return (((K + nk - 1) / nk) + 15) / 16 * 16;
+}
 
 int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   FpropParams p;
@@ -1187,13 +1216,7 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   choose_brick(a.N, a.Ho, a.Wo, kTileM, 1, &p.BW, &p.BH, &p.BNI);
   p.tiles_w = (a.Wo + p.BW - 1) / p.BW; p.tiles_h = (a.Ho + p.BH - 1) / p.BH; p.tiles_n = (a.N + p.BNI - 1) / p.BNI;
   p.cblocks = (a.C + kBlockK - 1) / kBlockK;
-  // Output-channel tile: up to 256 wide for the deep (tensor-bound) layers; layers with a short
-  // contraction are store-bound.
-  static const int env_cap = getenv("B2POSE_TC_BN_CAP") ? atoi(getenv("B2POSE_TC_BN_CAP")) : 0;
-  int bn_cap = 256;            // (measured: narrower tiles only add per-tile overhead, also for the 1x1 layers)
-  if (env_cap > 0) bn_cap = env_cap;
-  int nk = (a.K + bn_cap - 1) / bn_cap;
-  p.BN = (((a.K + nk - 1) / nk) + 15) / 16 * 16;
+  p.BN = choose_bn(a.K);
   p.tiles_k = (a.K + p.BN - 1) / p.BN;
   p.cblocks = (a.C + kBlockK - 1) / kBlockK;      // a ragged last block is zero-filled by TMA on the A side
   p.kblocks = a.R * a.S * p.cblocks;
@@ -1215,6 +1238,8 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.bn_sums = (p.tma_store && a.bn_sums && (p.tiles_k == 1 ? a.K <= 256 : multi_ok) && !no_fused_stats) ? a.bn_sums : nullptr;
   p.bn_totals = a.bn_totals;
   if (a.stats_fused) *a.stats_fused = p.bn_sums != nullptr;
+  p.b_mn = a.b_mn;
+  B2_REQUIRE(!p.b_mn || p.BN % 64 == 0, B2_E_UNSUPPORTED, "conv_tc: MN-major filter tiles need 64-channel groups");
   p.n_staging = kStaging;
   int extra = (p.bn_sums ? 64 * p.BN : 0);
   // Filter resident in shared memory when one channel tile covers K and the whole filter is small (layer1-type layers,
@@ -1247,7 +1272,8 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   int rc = a.vw_hp ? make_vw_map(&ma, a.act, a.N, a.vw_hp, a.vw_wp, a.Wo, p.BW, p.BH, p.BNI)
                    : make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
   if (rc) return rc;
-  rc = make_mat_map(&mb, a.filt, a.K, (long long)a.R * a.S * a.C, p.BN);
+  rc = p.b_mn ? make_mat_map(&mb, a.filt, a.C, (long long)a.R * a.S * a.K, 64)
+              : make_mat_map(&mb, a.filt, a.K, (long long)a.R * a.S * a.C, p.BN);
   if (rc) return rc;
   if (p.tma_store) {
     rc = make_act_map(&mo, a.out, a.N, a.out_H, a.out_W, a.K, p.BW, p.BH, p.BNI, 1);
@@ -1430,6 +1456,13 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   return B2_OK;
 }
 
+// stride-1 dgrad straight from the untransposed filter (MN-major B tiles of 64 output channels)
+static bool dgrad_direct(const B2ConvDesc* d) {
+  static const bool off = getenv("B2POSE_DGRAD_TRANSPOSE") && atoi(getenv("B2POSE_DGRAD_TRANSPOSE")) != 0;
+  return !off && d->stride == 1 && choose_bn(d->C) % 64 == 0 && !(d->flags & B2_CONV_W_PREPARED);
+}
+bool conv_tc_dgrad_needs_filter(const B2ConvDesc* d) { return !dgrad_direct(d); }
+
 // mode 0: transpose the filter into the workspace, then run; 1: ONLY the filter transposes, written to `workspace`
 // (b2_pconv_dgrad_filter: the weights are constant during a step, so callers hoist this off the backward critical
 // path); 2: `w` already is the buffer mode 1 produced (B2_CONV_W_PREPARED).
@@ -1453,6 +1486,16 @@ static int conv_tc_dgrad_impl(const B2ConvDesc* d, const void* dy, const float* 
   a.stride = 1;
   const int taps = d->R * d->S;
   dim3 tb(32, 8);
+  if (d->stride == 1 && dgrad_direct(d)) {
+    // dx = conv(dy, flipped/transposed filter), pad' = dil*(R-1) - pad -- the flip is a tap index and the transpose an
+    // MN-major B operand: the kernel reads W[k][tap][c] as it is (round 1 ran 86 transpose kernels per step)
+    if (mode == 1) return B2_OK;
+    a.filt = w; a.b_mn = 1;
+    a.R = d->R; a.S = d->S; a.dil = d->dil; a.pad = d->dil * (d->R - 1) - d->pad;
+    a.Ho = d->H; a.Wo = d->W; a.out_stride_sp = 1;
+    a.accumulate = (d->flags & B2_CONV_DX_ACCUMULATE) ? 1 : 0;
+    return run_conv_tc(a, st);
+  }
   if (d->stride == 1) {
     // dx = conv(dy, flipped/transposed filter), pad' = dil*(R-1) - pad
     TapMap tm;
