@@ -114,7 +114,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 // is not complete yet suspends the warp in front of its own MMAs) -- the predicates are consumed only at the end of
 // the block, so the poll latency overlaps the issue -- and (2) issues four MMAs and the commits under ONE elect.sync predicate
 // runs at the floor: 55 / 64 / 128 cycles per MMA for N = 64 / 128 / 256.
-constexpr uint32_t kPoll1 = 1, kPoll2 = 2, kCommit1 = 4, kCommit2 = 8;
+constexpr uint32_t kPoll1 = 1, kPoll2 = 2, kCommit1 = 4, kCommit2 = 8, kTwoMma = 16;    // kTwoMma: only the first two MMAs
 // Four MMAs D[tmem_d] (+)= A_k * B_k, k = 0..3, descriptors advancing by `dstep` (encoded >> 4 units) per k-step.
 // acc0: accumulate flag of the first MMA (the others always accumulate).  Must be executed by a converged warp.
 __device__ __forceinline__ void mma4_fused(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint64_t dstep, uint32_t idesc,
@@ -123,7 +123,7 @@ __device__ __forceinline__ void mma4_fused(uint32_t tmem_d, uint64_t adesc, uint
                                            uint32_t commit2_bar, uint32_t& ready1, uint32_t& ready2, uint64_t bstep) {
   asm volatile(
       "{\n\t"
-      ".reg .pred pw1, pw2, pe, pa, q1, q2, c1, c2;\n\t"
+      ".reg .pred pw1, pw2, pe, pa, q1, q2, c1, c2, p34;\n\t"
       ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
       ".reg .b32 t;\n\t"
       "and.b32 t, %8, 1;\n\tsetp.ne.b32 q1, t, 0;\n\t"
@@ -134,13 +134,14 @@ __device__ __forceinline__ void mma4_fused(uint32_t tmem_d, uint64_t adesc, uint
       "elect.sync _|pe, 0xffffffff;\n\t"
       "and.b32 t, %8, 4;\n\tsetp.ne.b32 c1, t, 0;\n\tand.pred c1, c1, pe;\n\t"
       "and.b32 t, %8, 8;\n\tsetp.ne.b32 c2, t, 0;\n\tand.pred c2, c2, pe;\n\t"
+      "and.b32 t, %8, 16;\n\tsetp.eq.b32 p34, t, 0;\n\tand.pred p34, p34, pe;\n\t"
       "setp.ne.b32 pa, %7, 0;\n\t"
       "add.s64 a1, %3, %5;\n\tadd.s64 a2, a1, %5;\n\tadd.s64 a3, a2, %5;\n\t"
       "add.s64 b1, %4, %15;\n\tadd.s64 b2, b1, %15;\n\tadd.s64 b3, b2, %15;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], %3, %4, %6, pa;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %6, 1;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a2, b2, %6, 1;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], a3, b3, %6, 1;\n\t"
+      "@p34 tcgen05.mma.cta_group::1.kind::f16 [%2], a2, b2, %6, 1;\n\t"
+      "@p34 tcgen05.mma.cta_group::1.kind::f16 [%2], a3, b3, %6, 1;\n\t"
       "@c1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t"
       "@c2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%14];\n\t"
       "selp.u32 %0, 1, 0, pw1;\n\tselp.u32 %1, 1, 0, pw2;\n\t"
@@ -236,6 +237,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major operand in a 64-byte-swizzled tile (layout type 4): rows of 64 bytes, `sbo_bytes` between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc64(uint32_t addr, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (4ull << 61);
+}
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 A/B
 __host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -251,6 +256,8 @@ struct FpropParams {
   int cblocks, kblocks;                                // C/64, taps*C/64
   int stages, tmem_cols;
   int b_resident;                                      // the whole filter (kblocks slices of BN rows) stays in shared memory
+  int k32;                                             // operand k-blocks of 32 elements in 64-byte-swizzled tiles (window-map
+                                                       // stems: 8-pixel windows) instead of 64 elements / 128-byte swizzle
   int b_mn;                                            // dgrad straight from the untransposed filter W[k][tap][c]: B tiles are
                                                        // MN-major atoms [64 k][64 c], taps read in flipped order
   int n_staging;                                       // 16 KB output staging buffers of the TMA-store epilogue (<= kStaging)
@@ -285,8 +292,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
-  const uint32_t stage_bytes = kABytes + (p.b_resident ? 0u : b_bytes);
+  const uint32_t kbe = p.k32 ? 32u : (uint32_t)kBlockK;              // elements per operand k-block
+  const uint32_t a_bytes = kTileM * kbe * 2, b_bytes = (uint32_t)p.BN * kbe * 2;
+  const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : b_bytes);
   // layout: [stages][A|B] | resident filter (b_resident: kblocks x B, the ring then holds A only) | kStaging x 16 KB
   //         output staging (TMA-store epilogue) | barriers | fp32 statistics [2*K]
   uint8_t* bres = smem + (size_t)p.stages * stage_bytes;
@@ -320,7 +328,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     // Converged warp; elect.sync inside produce_fused picks the issuing lane.  No divisions in the loop: (tap row,
     // tap column, channel block) advance as counters.
-    const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BNI) * kBlockK * 2;
+    const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BNI) * kbe * 2;
     if (p.b_resident && lane == 0 && !(p.debug & 24)) {
       // the filter is the same for every tile of this CTA (tiles_k == 1): fetch it once
       mbar_expect_tx(&bars->bfull, (uint32_t)p.kblocks * b_bytes);
@@ -329,12 +337,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (p.b_mn) {
           for (int a = 0; a < (p.BN >> 6); ++a)
             tma_load_2d(smem_u32(bres + (size_t)kb * b_bytes + a * 8192), &map_b, &bars->bfull,
-                        (p.R * p.S - 1 - tap) * p.K + a * 64, cb * kBlockK);
+                        (p.R * p.S - 1 - tap) * p.K + a * 64, cb * (int)kbe);
         } else {
           tma_load_2d(smem_u32(bres + (size_t)kb * b_bytes), &map_b, &bars->bfull, bcol, 0);
         }
-        bcol += kBlockK;
-        if (++cb == p.cblocks) { cb = 0; ++tap; bcol += p.C - p.cblocks * kBlockK; }
+        bcol += (int)kbe;
+        if (++cb == p.cblocks) { cb = 0; ++tap; bcol += p.C - p.cblocks * (int)kbe; }
       }
     }
     __syncwarp();
@@ -361,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               mbar_arrive(&bars->full[stage]);
             } else {                               // timing experiment: activation tile only (filter "resident")
               mbar_expect_tx(&bars->full[stage], a_box_bytes);
-              tma_load_4d(sa, &map_a, &bars->full[stage], cb * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, n0);
+              tma_load_4d(sa, &map_a, &bars->full[stage], cb * (int)kbe, iw0 + s * p.dil, ih0 + r * p.dil, n0);
             }
           }
           __syncwarp();
@@ -369,20 +377,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const bool has_next = kb + 1 < p.kblocks || more_tiles;
           const int mn_col = (p.R * p.S - 1 - (r * p.S + s)) * p.K + kt * p.BN;     // b_mn: flipped tap, first atom
           empty_ready = produce_fused((has_next ? 1u : 0u) | stage_flags, smem_u32(&bars->empty[nstage]), nphase ^ 1,
-                                      smem_u32(&bars->full[stage]), stage_tx, sa, &map_a, cb * kBlockK,
-                                      iw0 + s * p.dil, ih0 + r * p.dil, n0, sa + kABytes, &map_b,
-                                      p.b_mn ? mn_col : bcol, p.b_mn ? cb * kBlockK : kt * p.BN);
+                                      smem_u32(&bars->full[stage]), stage_tx, sa, &map_a, cb * (int)kbe,
+                                      iw0 + s * p.dil, ih0 + r * p.dil, n0, sa + a_bytes, &map_b,
+                                      p.b_mn ? mn_col : bcol, p.b_mn ? cb * (int)kbe : kt * p.BN);
           if (p.b_mn && !p.b_resident && p.BN > 64) {
             if (elect_one())
               for (int a = 1; a < (p.BN >> 6); ++a)
-                tma_load_2d(sa + kABytes + a * 8192, &map_b, &bars->full[stage], mn_col + a * 64, cb * kBlockK);
+                tma_load_2d(sa + a_bytes + a * 8192, &map_b, &bars->full[stage], mn_col + a * 64, cb * (int)kbe);
             __syncwarp();
           }
         }
-        bcol += kBlockK;
+        bcol += (int)kbe;
         if (++cb == p.cblocks) {
           cb = 0;
-          bcol += p.C - p.cblocks * kBlockK;       // ragged last channel block: the next tap starts at tap * C
+          bcol += p.C - p.cblocks * (int)kbe;      // ragged last channel block: the next tap starts at tap * C
           if (++s == p.S) { s = 0; ++r; }
         }
         stage = nstage;
@@ -419,11 +427,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t flags = ((!last || more_tiles) ? kPoll1 : 0u) | ((last && more_tiles) ? kPoll2 : 0u) | kCommit1 |
                                (last ? kCommit2 : 0u);
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t sb = p.b_resident ? smem_u32(bres + (size_t)kb * b_bytes) : sa + kABytes;
+        const uint32_t sb = p.b_resident ? smem_u32(bres + (size_t)kb * b_bytes) : sa + a_bytes;
         // B: K-major filter slice [BN][64], or (b_mn) BN / 64 MN-major atoms [64 k][64 c] straight from the
-        // untransposed filter: LBO = one 8 KB atom, 16 k-rows per MMA = 2048 B
-        const uint64_t bdesc = p.b_mn ? smem_desc(sb, 8192, 1024) : smem_desc(sb, 0, 1024);
-        mma4_fused(tmem_d, smem_desc(sa, 0, 1024), bdesc, 2ull, idesc, (uint32_t)kb, flags,
+        // untransposed filter: LBO = one 8 KB atom, 16 k-rows per MMA = 2048 B; k32: 64-byte rows in 64-byte-swizzled
+        // tiles (8-row groups 512 B apart), two MMAs per stage
+        const uint64_t bdesc = p.k32 ? smem_desc64(sb, 512) : (p.b_mn ? smem_desc(sb, 8192, 1024) : smem_desc(sb, 0, 1024));
+        const uint64_t adesc = p.k32 ? smem_desc64(sa, 512) : smem_desc(sa, 0, 1024);
+        mma4_fused(tmem_d, adesc, bdesc, 2ull, idesc, (uint32_t)kb, flags | (p.k32 ? kTwoMma : 0u),
                    smem_u32(&bars->full[nstage]), nphase, smem_u32(&bars->tempty[nacc]), nacc_parity,
                    smem_u32(&bars->empty[stage]), smem_u32(&bars->tfull[acc]), full_ready, acc_ready,
                    p.b_mn ? 128ull : 2ull);
@@ -1040,11 +1050,11 @@ __global__ void __launch_bounds__(256) vw_pad_kernel(const bf16* __restrict__ x,
     *reinterpret_cast<uint2*>(dst + (long long)wp * 4) = make_uint2(lo, hi);
   }
 }
-// Wk[k][r][4 p + c] = W[k][r][p - 1][c]
-__global__ void vw_filter_kernel(const bf16* __restrict__ w, bf16* __restrict__ wk, int K, int C) {
-  const int total = K * 7 * 64;
+// Wk[k][r][4 p + c] = W[k][r][p - 1][c]   (win = 64 or 32 window elements per filter row)
+__global__ void vw_filter_kernel(const bf16* __restrict__ w, bf16* __restrict__ wk, int K, int C, int win) {
+  const int total = K * 7 * win;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int j = i & 63, r = (i >> 6) % 7, k = i / (7 * 64);
+    const int j = i % win, r = (i / win) % 7, k = i / (7 * win);
     const int pp = j >> 2, c = j & 3, s2 = pp - 1;
     bf16 v = __float2bfloat16(0.f);
     if (s2 >= 0 && s2 < 7 && c < C) v = w[((long long)k * 49 + r * 7 + s2) * C + c];
@@ -1115,16 +1125,17 @@ int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, i
 // 4-D window map over the zero-bordered stem input xp[N][Hp][Wp][4]: dims (64-element window, output column, padded
 // row, image), strides (16 B per output column, one padded row, one padded image); box (64, bw, 2 bh, bni) with element
 // stride 2 along the rows (vertical stride of the stem)
-int make_vw_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp, int Wo, int bw, int bh, int bni) {
+// (win = 64: 16-pixel windows, 128-byte swizzle; win = 32: 8-pixel windows -- all a 7-tap row needs -- 64-byte swizzle)
+int make_vw_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp, int Wo, int bw, int bh, int bni, int win = 64) {
   EncodeTiledFn fn = encode_fn();
   B2_REQUIRE(fn != nullptr, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Hp, (cuuint64_t)N};
+  cuuint64_t dims[4] = {(cuuint64_t)win, (cuuint64_t)Wo, (cuuint64_t)Hp, (cuuint64_t)N};
   cuuint64_t strides[3] = {16, (cuuint64_t)Wp * 8, (cuuint64_t)Hp * Wp * 8};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)(bh * 2), (cuuint32_t)bni};
+  cuuint32_t box[4] = {(cuuint32_t)win, (cuuint32_t)bw, (cuuint32_t)(bh * 2), (cuuint32_t)bni};
   cuuint32_t estr[4] = {1, 1, 2, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, win == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B2_REQUIRE(r == CUDA_SUCCESS, B2_E_LAUNCH,
              "conv_tc: cuTensorMapEncodeTiled(stem window map N=%d Hp=%d Wp=%d Wo=%d box %dx%dx%d) failed: %d", N, Hp, Wp,
              Wo, bni, bh, bw, (int)r);
@@ -1132,16 +1143,16 @@ int make_vw_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp, int Wo,
 }
 
 // 2-D map over a [rows, cols] bf16 matrix, box (64, box_rows)
-int make_mat_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+int make_mat_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows, int box_cols = 64) {
   EncodeTiledFn fn = encode_fn();
   B2_REQUIRE(fn != nullptr, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B2_REQUIRE(r == CUDA_SUCCESS, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled(matrix %lldx%lld box %d) failed: %d", rows,
              cols, box_rows, (int)r);
   return B2_OK;
@@ -1194,6 +1205,7 @@ struct RunArgs {
   int pad_w, use_pad_w;                                        // pad_w is read only when use_pad_w != 0
   int vw_hp, vw_wp;                                            // != 0: `act` is a window-map stem input (make_vw_map)
   int b_mn;                                                    // filt is the UNtransposed filter [C][R*S*K] (dgrad, see FpropParams)
+  int k32;                                                     // 32-element k-blocks, 64-byte swizzle (window-map stems)
   int accumulate;                                              // dgrad: reduce-add into `out`
   float* bn_sums; bool* stats_fused; int bn_totals;           // optional fused BatchNorm statistics
   int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
@@ -1215,12 +1227,14 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.stride = a.stride; p.pad = a.pad; p.dil = a.dil; p.Ho = a.Ho; p.Wo = a.Wo;
   choose_brick(a.N, a.Ho, a.Wo, kTileM, 1, &p.BW, &p.BH, &p.BNI);
   p.tiles_w = (a.Wo + p.BW - 1) / p.BW; p.tiles_h = (a.Ho + p.BH - 1) / p.BH; p.tiles_n = (a.N + p.BNI - 1) / p.BNI;
-  p.cblocks = (a.C + kBlockK - 1) / kBlockK;
   p.BN = choose_bn(a.K);
   p.tiles_k = (a.K + p.BN - 1) / p.BN;
-  p.cblocks = (a.C + kBlockK - 1) / kBlockK;      // a ragged last block is zero-filled by TMA on the A side
+  const int kbe = a.k32 ? 32 : kBlockK;
+  p.k32 = a.k32;
+  p.cblocks = (a.C + kbe - 1) / kbe;               // a ragged last block is zero-filled by TMA on the A side
   p.kblocks = a.R * a.S * p.cblocks;
-  int stage_bytes = (int)kABytes + p.BN * kBlockK * 2;
+  const int a_stage_bytes = kTileM * kbe * 2;
+  int stage_bytes = a_stage_bytes + p.BN * kbe * 2;
   static const bool no_tma_store = getenv("B2POSE_TC_NO_TMA_STORE") != nullptr;      // tuning switches
   static const bool no_fused_stats = getenv("B2POSE_TC_NO_FUSED_STATS") != nullptr;
   p.tma_store = (p.BN % 64 == 0 && a.out_stride_sp == 1 && !a.bias && !no_tma_store) ? 1 : 0;   // bias: direct-store path
@@ -1246,11 +1260,11 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   // the stems): the ring then carries activation tiles only -- a third to two thirds less L2 -> SM traffic per tile and
   // a deeper ring, which is what bounds these layers (B2POSE_TC_B_RESIDENT=0 disables)
   static const bool allow_resident = !(getenv("B2POSE_TC_B_RESIDENT") && atoi(getenv("B2POSE_TC_B_RESIDENT")) == 0);
-  const int filt_bytes = p.kblocks * p.BN * kBlockK * 2;
+  const int filt_bytes = p.kblocks * p.BN * kbe * 2;
   p.b_resident = (allow_resident && p.tiles_k == 1 && filt_bytes <= 96 * 1024 &&
                   (long long)p.tiles_w * p.tiles_h * p.tiles_n >= 2LL * b2_num_sms()) ? 1 : 0;
   if (p.b_resident) {
-    stage_bytes = (int)kABytes;
+    stage_bytes = a_stage_bytes;
     extra += filt_bytes;
     if (p.BN <= 64) p.n_staging = 2;           // two sets of one buffer: room for two more activation stages
   }
@@ -1269,11 +1283,12 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.pad_w = a.use_pad_w ? a.pad_w : a.pad;
   p.stride_w = a.vw_hp ? 1 : a.stride;
   CUtensorMap ma, mb, mo;
-  int rc = a.vw_hp ? make_vw_map(&ma, a.act, a.N, a.vw_hp, a.vw_wp, a.Wo, p.BW, p.BH, p.BNI)
+  B2_REQUIRE(!a.k32 || (a.vw_hp && !a.b_mn), B2_E_UNSUPPORTED, "conv_tc: 32-element k-blocks are a window-map stem mode");
+  int rc = a.vw_hp ? make_vw_map(&ma, a.act, a.N, a.vw_hp, a.vw_wp, a.Wo, p.BW, p.BH, p.BNI, kbe)
                    : make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
   if (rc) return rc;
   rc = p.b_mn ? make_mat_map(&mb, a.filt, a.C, (long long)a.R * a.S * a.K, 64)
-              : make_mat_map(&mb, a.filt, a.K, (long long)a.R * a.S * a.C, p.BN);
+              : make_mat_map(&mb, a.filt, a.K, (long long)a.R * a.S * a.C, p.BN, kbe);
   if (rc) return rc;
   if (p.tma_store) {
     rc = make_act_map(&mo, a.out, a.N, a.out_H, a.out_W, a.K, p.BW, p.BH, p.BNI, 1);
@@ -1318,6 +1333,12 @@ inline bool is_stem(const B2ConvDesc* d) { return d->C <= 4 && d->R * d->S * d->
 inline bool is_vw_stem(const B2ConvDesc* d) {
   static const int im2col = getenv("B2POSE_STEM_IM2COL") ? atoi(getenv("B2POSE_STEM_IM2COL")) : 0;
   return !im2col && is_stem(d) && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->dil == 1;
+}
+// fprop reads 8-pixel windows (32 elements, 64-byte swizzle): half the operand traffic and MMAs of the 16-pixel
+// window; B2POSE_STEM_WIN64=1 selects the 128-byte-swizzle variant (the wgrad kernel uses it)
+inline bool vw_fprop_k32() {
+  static const bool win64 = getenv("B2POSE_STEM_WIN64") && atoi(getenv("B2POSE_STEM_WIN64")) != 0;
+  return !win64;
 }
 inline int vw_hp(const B2ConvDesc* d) { return d->H + 6; }
 inline int vw_wp(const B2ConvDesc* d) { return (d->W + 17) / 2 * 2; }      // even (16-byte row pitch), >= W + 16
@@ -1404,10 +1425,11 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
     // B2_CONV_X_PREMASKED: the caller's x is zero wherever the mask is (network stems: veil = depth != 0)
     int rc = launch_vw_pad(d, x, (partial && !premasked) ? mask_in : nullptr, xp, st);
     if (rc) return rc;
-    vw_filter_kernel<<<(d->K * 7 * 64 + 255) / 256, 256, 0, st>>>((const bf16*)w, wk, d->K, d->C);
+    const int win = vw_fprop_k32() ? 32 : 64;
+    vw_filter_kernel<<<(d->K * 7 * win + 255) / 256, 256, 0, st>>>((const bf16*)w, wk, d->K, d->C, win);
     B2_LAUNCH_CHECK("vw_filter");
-    a.act = xp; a.vw_hp = vw_hp(d); a.vw_wp = vw_wp(d);
-    a.H = vw_hp(d); a.W = d->Wo; a.C = 64; a.filt = wk; a.R = 7; a.S = 1; a.stride = 2; a.pad = 0; a.dil = 1;
+    a.act = xp; a.vw_hp = vw_hp(d); a.vw_wp = vw_wp(d); a.k32 = win == 32;
+    a.H = vw_hp(d); a.W = d->Wo; a.C = win; a.filt = wk; a.R = 7; a.S = 1; a.stride = 2; a.pad = 0; a.dil = 1;
     a.pad_w = 0; a.use_pad_w = 1;
     if (partial) {
       // a 7x7 window is 49 mask loads per output pixel: do the mask algebra once in its own small
