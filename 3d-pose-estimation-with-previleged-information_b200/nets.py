@@ -284,7 +284,13 @@ class ResNet(nn.Module):
         # f = input of layer3: the boundary between the shallow (stems, layer1/2/5/6, fusion) and the deep part; a
         # data-parallel Trainer runs the backward pass in two stages around it so that the all-reduce of the deep
         # gradients (~90 % of the parameters) overlaps the shallow backward (trainer.Trainer._fwd_bwd_deep)
-        self._boundary = f if getattr(self, "_mark_boundary", False) else None
+        self._boundary = None
+        if getattr(self, "_mark_boundary", False):
+            # cut the autograd graph here: stage 1 runs loss.backward() down to the detached leaf, stage 2 continues
+            # from `f` with the leaf's gradient (backward(inputs=[f]) would also RUN the node that produced f, and the
+            # second stage would then accumulate that node's parameter gradients twice)
+            cut = f.detach().requires_grad_()
+            self._boundary, f = (f, cut), cut
         m, _ = self._run(self.layer3, f, None)
         n, _ = self._run(self.layer4, torch.relu(m) if self.skip_relu else m, None)
         top = torch.relu(n) if self.skip_relu else n

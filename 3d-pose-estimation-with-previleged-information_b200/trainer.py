@@ -187,6 +187,9 @@ class Trainer:
         self.pg = process_group
         self.world = 1
         self.overlap = False
+        self.buckets = None
+        self._force_two = __import__("os").environ.get("B2POSE_FORCE_TWO_STAGE", "0") != "0"
+        self.comm_sms = 0
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             import torch.distributed as dist
             self.pg = process_group if process_group is not None else dist.group.WORLD
@@ -205,9 +208,6 @@ class Trainer:
             deep = [(o, o + (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN)
                     for name, p, o in zip(self.list_names, self.flat.params, self.flat.offsets)
                     if name.startswith(("layer3.", "layer4.", "regressor.", "cam_regressor.", "mat_regressor."))]
-            # deep parameters that autograd (not a kernel sink) accumulates: the regressors' plain convolutions
-            self.deep_params = [p for name, p in zip(self.list_names, self.flat.params)
-                                if name.startswith(("regressor.", "cam_regressor.", "mat_regressor."))]
             bucket_mb = float(env.get("B2POSE_BUCKET_MB", bucket_mb))
             self.buckets = GradBuckets(self.flat, self.pg, bucket_mb, deep=deep if self.overlap else None,
                                        compress=compress)
@@ -329,7 +329,10 @@ class Trainer:
 
     # ---- data parallel: backward in two stages around the input of layer3 (see nets.ResNet.forward) ----
     def _two_stage(self, semi):
-        return self.overlap and self.world > 1 and semi is None and self.teacher is None
+        if semi is not None or self.teacher is not None:
+            return False
+        # (B2POSE_FORCE_TWO_STAGE=1: run the staged backward in a single process too -- tools/two_stage_check.py)
+        return (self.overlap and self.world > 1) or self._force_two
 
     def _fwd_bwd_deep(self, batch):
         """Stage 1: zero-grad, forward, head, loss, backward down to the input of layer3.  On return every gradient of
@@ -340,13 +343,9 @@ class Trainer:
         self.model._mark_boundary = True
         try:
             loss, spec = self._forward_loss(*batch)
-            f = self.model._boundary
+            f, cut = self.model._boundary
             ops.wgrad_overlap_sync(self.device)
-            # (parameters whose kernels do not write into the flat buffer themselves -- the regressor's plain ConvFn --
-            #  are accumulated by autograd: name them, torch.autograd.backward(inputs=...) skips everything else)
-            # retain_graph: without it the engine frees the saved tensors of the whole graph, including the shallow
-            # nodes it did not run; the second stage releases everything
-            torch.autograd.backward([loss], inputs=[f] + self.deep_params, retain_graph=True)
+            loss.backward()                      # stops at the detached leaf `cut` (nets.ResNet.forward)
             ops.wgrad_overlap_join(self.device)
         except BaseException:
             ops.wgrad_overlap_end(self.device)
@@ -355,8 +354,7 @@ class Trainer:
         finally:
             self.model._mark_boundary = False
             self.model._boundary = None
-        self._stage2 = (f, f.grad)
-        f.grad = None
+        self._stage2 = (f, cut.grad)
         return loss.detach(), spec
 
     def _bwd_shallow(self):
@@ -486,9 +484,11 @@ class Trainer:
             else:
                 entry["fb"].replay()
                 if entry.get("fb2") is not None:     # two-stage backward: deep buckets travel beside the shallow stage
-                    self.buckets.start_deep()
+                    if self.buckets is not None:
+                        self.buckets.start_deep()
                     entry["fb2"].replay()
-                    self.buckets.finish()
+                    if self.buckets is not None:
+                        self.buckets.finish()
                 elif dist_on:
                     self.buckets.allreduce()
                 entry["up"].replay()
@@ -502,9 +502,11 @@ class Trainer:
     def _eager_step(self, st, st_semi, two):
         if two:
             loss, spec = self._fwd_bwd_deep(st)
-            self.buckets.start_deep()
+            if self.buckets is not None:
+                self.buckets.start_deep()
             self._bwd_shallow()
-            self.buckets.finish()
+            if self.buckets is not None:
+                self.buckets.finish()
         else:
             loss, spec = self._fwd_bwd(st, st_semi)
             if self.world > 1:

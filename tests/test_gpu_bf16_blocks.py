@@ -11,8 +11,8 @@ ORACLE's input and output gradient and must reproduce
 
   * its output within 2e-2 relative (max|a-b| / max|b|, the bf16 bound of north_star; measured <= 0.7e-2),
   * the updated veil bit-exactly,
-  * its input gradient within 3e-2 in relative L2 norm, with at least 99.9 % of the elements within 3e-2 of max|ref|
-    (measured: L2 <= 2.4e-2, 99.9 % quantile <= 2.8e-2).  The remaining <= 1e-4 of the elements are ReLU-gate flips: a
+  * its input gradient within 5e-2 in relative L2 norm (measured <= 2.9e-2: the L2 norm is dominated by the outliers below),
+    with at least 99.9 % of the elements within 3e-2 of max|ref| (measured: 99.9 % quantile <= 2.8e-2).  The remaining <= 1e-4 of the elements are ReLU-gate flips: a
     pre-activation within rounding distance of zero is gated differently on the two sides, which switches one whole
     term of that pixel's sum on or off (the device and the oracle share every formula, not the summation order),
   * every parameter gradient within 3e-2 in norm (measured <= 0.3e-2) and 8e-2 in relative L2 norm (measured <= 5.2e-2,
@@ -30,7 +30,7 @@ from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL, TOL_GRAD, TOL_L2 = 2e-2, 3e-2, 8e-2
+TOL, TOL_GRAD, TOL_L2, TOL_DX = 2e-2, 3e-2, 8e-2, 5e-2
 
 
 def _fused(kind):
@@ -78,7 +78,7 @@ def _check_dx(unit_name, got_nhwc, want, worst):
     frac = float((d > TOL_GRAD * float(want.abs().max())).float().mean())
     worst["dx"] = max(worst["dx"], l2)
     worst["dx_out"] = max(worst["dx_out"], frac)
-    assert l2 < TOL_GRAD and frac < 1e-3, (unit_name, "dx", l2, frac)
+    assert l2 < TOL_DX and frac < 1e-3, (unit_name, "dx", l2, frac)
 
 
 def _run_units(b2pose, dev, kind, model, side, n, seed_w=41, seed_b=9):

@@ -8,7 +8,9 @@ ranks (the mean is folded into the fused Adam kernel).  Each rank steps on its o
     compressed exchange of the bf16 mode (run with the deterministic BatchNorm reductions, B2POSE_BN_TOTALS=0: on this
     batch-2 fixture the order of the fp32 atomics alone moves the bf16 gradients by 10-20 %),
   * both ranks hold identical weights after the step (eager and CUDA-graph mode, plain and two-stage overlapped
-    exchange).
+    exchange),
+  * (single GPU) the two-stage backward pass of the overlapped mode -- the autograd graph cut at the input of layer3 --
+    yields the gradients of the plain backward pass, eagerly and replayed from its two CUDA graphs.
 """
 import os
 import socket
@@ -92,3 +94,37 @@ def test_two_rank_step(tmp_path, half, overlap, use_graph):
     err = float((a["g"] - total).norm() / total.norm())
     print("half", half, "overlap", overlap, "reduced-gradient L2 error vs sum of per-rank gradients: %.2e" % err)
     assert err < (1e-2 if half else 1e-4)
+
+
+def _one_trainer(b2, dev, kind, two, use_graph, steps):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pose_oracle as po
+    fused = kind == "partial_fusionnet"
+    cfg = po.net_config(side_in=64, num_joints=17, depth_only=not fused)
+    net = getattr(b2, kind).resnet18(cfg, False)
+    net.load_state_dict(po.init_state(kind, "resnet18", cfg, seed=5))
+    # learning rate 0: the weights stay put, so every step (eager warm-up or graph replay) computes the same gradient
+    args = b2.train_args(model="resnet18", num_joints=17, side_in=64, depth_only=not fused, do_fusion=fused, half_acc=False,
+                         learn_rate=0.0, weight_decay=0.0, warmup=0)
+    tr = b2.Trainer(args, net.to(dev).train(), dict(key_index=16), use_graph=use_graph)
+    tr._force_two = two
+    batch = tuple(t.to(dev) for t in po.synth_batch(4, 64, 17, seed=20))
+    for _ in range(steps):
+        tr.train_step(batch)
+    torch.cuda.synchronize()
+    return tr.flat.g.clone()
+
+
+@pytest.mark.parametrize("kind", ["partial_fusionnet", "partial_depthnet"])
+def test_staged_backward_matches_plain(b2pose, dev, kind):
+    """fp32 (deterministic up to the order of the weight-gradient atomics): every parameter's gradient, including the
+    node that PRODUCES the boundary tensor, must come out of the staged pass once -- not zero, not twice."""
+    plain = _one_trainer(b2pose, dev, kind, False, False, 1)
+    staged = _one_trainer(b2pose, dev, kind, True, False, 1)
+    err = float((staged - plain).norm() / plain.norm())
+    print(kind, "staged vs plain backward, eager, step 1: %.2e" % err)
+    assert err < 1e-5
+    staged5 = _one_trainer(b2pose, dev, kind, True, True, 5)          # 3 eager warm-ups, capture, 1 replay of fb + fb2
+    err = float((staged5 - plain).norm() / plain.norm())
+    print(kind, "staged (replayed from its two CUDA graphs) vs plain eager: %.2e" % err)
+    assert err < 1e-5
