@@ -95,6 +95,9 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier_group(int grp) {          // four-warp epilogue groups: barriers 2 and 3
+  asm volatile("bar.sync %0, 128;" ::"r"(grp + 2) : "memory");
+}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -150,6 +153,42 @@ __device__ __forceinline__ void mma4_fused(uint32_t tmem_d, uint64_t adesc, uint
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "l"(dstep), "r"(idesc), "r"(acc0), "r"(flags), "r"(poll1_bar),
         "r"(poll1_parity), "r"(poll2_bar), "r"(poll2_parity), "r"(commit1_bar), "r"(commit2_bar), "l"(bstep)
       : "memory");
+}
+// Row stems: the fourteen MMAs of one tile (seven tap rows x two K = 16 steps) in ONE block -- the cost of a block
+// (elect, predicate set-up, the barrier polls) is paid per block, not per MMA.  Descriptors in 16-byte units: the A
+// operand of tap row r starts `arow` units after row r - 1, the filter slice `brow` units; the second K step is 2 units
+// (32 bytes) further in both.  Polls / commits as in mma4_fused (kPoll1 | kPoll2 in `flags`; both commits always).
+__device__ __forceinline__ void mma14_rows(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint64_t arow, uint64_t brow,
+                                           uint32_t idesc, uint32_t flags, uint32_t poll1_bar, uint32_t poll1_parity,
+                                           uint32_t poll2_bar, uint32_t poll2_parity, uint32_t commit1_bar,
+                                           uint32_t commit2_bar, uint32_t& ready1, uint32_t& ready2) {
+#define B2_ROW_MMAS(ACC)                                                                   \
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], ad, bd, %7, " ACC ";\n\t"                  \
+  "add.s64 ad2, ad, 2;\n\tadd.s64 bd2, bd, 2;\n\t"                                        \
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%2], ad2, bd2, %7, 1;\n\t"                      \
+  "add.s64 ad, ad, %5;\n\tadd.s64 bd, bd, %6;\n\t"
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pw1, pw2, pe, pz, q1, q2;\n\t"
+      ".reg .b64 ad, bd, ad2, bd2;\n\t"
+      ".reg .b32 t;\n\t"
+      "and.b32 t, %8, 1;\n\tsetp.ne.b32 q1, t, 0;\n\t"
+      "and.b32 t, %8, 2;\n\tsetp.ne.b32 q2, t, 0;\n\t"
+      "setp.ne.b32 pw1, 0, 0;\n\tsetp.ne.b32 pw2, 0, 0;\n\tsetp.ne.b32 pz, 0, 0;\n\t"
+      "@q1 mbarrier.test_wait.parity.shared::cta.b64 pw1, [%9], %10;\n\t"
+      "@q2 mbarrier.test_wait.parity.shared::cta.b64 pw2, [%11], %12;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "mov.b64 ad, %3;\n\tmov.b64 bd, %4;\n\t"
+      B2_ROW_MMAS("pz") B2_ROW_MMAS("1") B2_ROW_MMAS("1") B2_ROW_MMAS("1") B2_ROW_MMAS("1") B2_ROW_MMAS("1") B2_ROW_MMAS("1")
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%14];\n\t"
+      "selp.u32 %0, 1, 0, pw1;\n\tselp.u32 %1, 1, 0, pw2;\n\t"
+      "}"
+      : "=r"(ready1), "=r"(ready2)
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "l"(arow), "l"(brow), "r"(idesc), "r"(flags), "r"(poll1_bar),
+        "r"(poll1_parity), "r"(poll2_bar), "r"(poll2_parity), "r"(commit1_bar), "r"(commit2_bar)
+      : "memory");
+#undef B2_ROW_MMAS
 }
 // Producer counterpart of mma4_fused: the single producing thread's serial latency per ring stage (a blocking wait on
 // `empty`, two integer divisions, two TMA issues wrapped in ELECT loops: ~400-600 cycles) bounded the shallow layers
@@ -241,6 +280,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 __device__ __forceinline__ uint64_t smem_desc64(uint32_t addr, uint32_t sbo_bytes) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (4ull << 61);
 }
+// K-major operand WITHOUT swizzle (layout type 0): 8-row x 16-byte core matrices; `lbo_bytes` between core matrices that
+// are neighbours along K, `sbo_bytes` between neighbours along M.  The strides need not tile the buffer: the row stems
+// address overlapping windows of one raw input row this way (lbo 16, sbo 128, see FpropParams::vw_rows)
+__device__ __forceinline__ uint64_t smem_desc_plain(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 A/B
 __host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -258,9 +304,17 @@ struct FpropParams {
   int b_resident;                                      // the whole filter (kblocks slices of BN rows) stays in shared memory
   int k32;                                             // operand k-blocks of 32 elements in 64-byte-swizzled tiles (window-map
                                                        // stems: 8-pixel windows) instead of 64 elements / 128-byte swizzle
+  int vw_rows;                                         // row stems (7x7, stride 2, input padded to 4 channels): a tile is 128
+                                                       // pixels of ONE output row; its stage holds the seven raw input rows
+                                                       // [7][kVwRowPitch] once, and the A operand of tap row r is a no-swizzle
+                                                       // descriptor over row r whose 16-byte chunks OVERLAP between pixels
+                                                       // (pixel m, chunk c -> raw chunk m + c): no im2col copy anywhere
   int b_mn;                                            // dgrad straight from the untransposed filter W[k][tap][c]: B tiles are
                                                        // MN-major atoms [64 k][64 c], taps read in flipped order
   int n_staging;                                       // 16 KB output staging buffers of the TMA-store epilogue (<= kStaging)
+  int epi_split;                                       // the eight epilogue warps work as two groups of four on ALTERNATE
+                                                       // tiles (group = TMEM accumulator buffer): two epilogue latency
+                                                       // chains in flight instead of one (narrow tiles, BN <= 128)
   int scale_mode;                                      // 0 none, 1 partial-conv ratio from mask_in, 2 row_scale[]
   int mask_R, mask_S, mask_stride, mask_pad, mask_dil, mask_H, mask_W;   // window geometry for mode 1
   const float* mask_in;
@@ -280,11 +334,14 @@ struct FpropParams {
   int bn_totals;                                       // bn_sums is one pre-zeroed float[2*K]: add with fp32 reductions
 };
 
+constexpr uint32_t kVwRowChunks = 9, kVwRowPitch = kVwRowChunks * 256;   // raw stem row in a stage: 9 x 256 B >= 131 x 16 B
+
 struct __align__(8) PipeBars {
   uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2], bfull;
   uint32_t tmem_base;
 };
 
+template <bool kSplit>              // kSplit: FpropParams::epi_split, compiled in (a run-time switch cost the wide tiles 10-50 %)
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const FpropParams p) {
@@ -292,8 +349,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t kbe = p.k32 ? 32u : (uint32_t)kBlockK;              // elements per operand k-block
-  const uint32_t a_bytes = kTileM * kbe * 2, b_bytes = (uint32_t)p.BN * kbe * 2;
+  const uint32_t kbe = (p.k32 || p.vw_rows) ? 32u : (uint32_t)kBlockK;              // elements per operand k-block
+  const uint32_t a_bytes = p.vw_rows ? (uint32_t)kABytes : kTileM * kbe * 2, b_bytes = (uint32_t)p.BN * kbe * 2;
   const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : b_bytes);
   // layout: [stages][A|B] | resident filter (b_resident: kblocks x B, the ring then holds A only) | kStaging x 16 KB
   //         output staging (TMA-store epilogue) | barriers | fp32 statistics [2*K]
@@ -310,7 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kSplit ? 4 : 8); }
     mbar_init(&bars->bfull, 1);
     fence_barrier_init();
     prefetch_map(&map_a);
@@ -328,7 +385,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     // Converged warp; elect.sync inside produce_fused picks the issuing lane.  No divisions in the loop: (tap row,
     // tap column, channel block) advance as counters.
-    const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BNI) * kbe * 2;
+    const uint32_t a_box_bytes = p.vw_rows ? 7u * kVwRowPitch : (uint32_t)(p.BW * p.BH * p.BNI) * kbe * 2;
+    const int ring_kblocks = p.vw_rows ? 1 : p.kblocks;               // ring stages per tile
     if (p.b_resident && lane == 0 && !(p.debug & 24)) {
       // the filter is the same for every tile of this CTA (tiles_k == 1): fetch it once
       mbar_expect_tx(&bars->bfull, (uint32_t)p.kblocks * b_bytes);
@@ -353,10 +411,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int kt = tile % p.tiles_k, mt = tile / p.tiles_k;
       const int wi = mt % p.tiles_w, hi = (mt / p.tiles_w) % p.tiles_h, ni = mt / (p.tiles_w * p.tiles_h);
-      const int iw0 = wi * p.BW * p.stride_w - p.pad_w, ih0 = hi * p.BH * p.stride - p.pad, n0 = ni * p.BNI;
+      // (row stems: 256-byte units of the padded row -- 128 output pixels are 8 of them)
+      const int iw0 = p.vw_rows ? wi * 8 : wi * p.BW * p.stride_w - p.pad_w, ih0 = hi * p.BH * p.stride - p.pad, n0 = ni * p.BNI;
       const bool more_tiles = tile + (int)gridDim.x < total_tiles;
       int r = 0, s = 0, cb = 0, bcol = 0;                 // bcol = tap * C + cb * 64
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      for (int kb = 0; kb < ring_kblocks; ++kb) {
         if (!empty_ready) mbar_wait(&bars->empty[stage], phase ^ 1);
         int nstage = stage + 1;
         uint32_t nphase = phase;
@@ -374,7 +433,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           __syncwarp();
         } else {
-          const bool has_next = kb + 1 < p.kblocks || more_tiles;
+          const bool has_next = kb + 1 < ring_kblocks || more_tiles;
           const int mn_col = (p.R * p.S - 1 - (r * p.S + s)) * p.K + kt * p.BN;     // b_mn: flipped tap, first atom
           empty_ready = produce_fused((has_next ? 1u : 0u) | stage_flags, smem_u32(&bars->empty[nstage]), nphase ^ 1,
                                       smem_u32(&bars->full[stage]), stage_tx, sa, &map_a, cb * (int)kbe,
@@ -417,6 +476,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool more_tiles = tile + (int)gridDim.x < total_tiles;
       const int nacc = (local + 1) & 1;
       const uint32_t nacc_parity = (((local + 1) >> 1) & 1) ^ 1;
+      if (p.vw_rows) {
+        // one stage = the tile's seven raw input rows; tap row r: two K=16 MMAs over the overlapping 16-byte chunks of
+        // raw row r (pixel m, chunk c at (m + c) * 16: K-neighbours 16 B apart, 8-pixel groups 128 B apart)
+        if (!full_ready) mbar_wait(&bars->full[stage], phase);
+        tc_fence_after();
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        mma14_rows(tmem_d, smem_desc_plain(sa, 16, 128), smem_desc64(smem_u32(bres), 512), (uint64_t)(kVwRowPitch >> 4),
+                   (uint64_t)(b_bytes >> 4), idesc, more_tiles ? (kPoll1 | kPoll2) : 0u, smem_u32(&bars->full[nstage]), nphase,
+                   smem_u32(&bars->tempty[nacc]), nacc_parity, smem_u32(&bars->empty[stage]), smem_u32(&bars->tfull[acc]),
+                   full_ready, acc_ready);
+        stage = nstage;
+        phase = nphase;
+        continue;
+      }
       for (int kb = 0; kb < p.kblocks; ++kb) {
         if (!full_ready) mbar_wait(&bars->full[stage], phase);
         tc_fence_after();
@@ -446,9 +522,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Two warps per TMEM lane quarter: warp (q, half) owns rows 32q..32q+31 and the `half` 32-column
     // part of every 64-column group.
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;
+    constexpr bool split = kSplit;                // two four-warp groups on alternate tiles (FpropParams::epi_split)
+    const int grp = split ? (warp - 2) >> 2 : 0;
+    const int half = split ? 0 : (warp - 2) >> 2; // (split: a warp converts both 32-column halves of a group)
     const int ew = warp - 2;                      // epilogue warp index 0..7
-    const int ep_tid = threadIdx.x - 64;          // 0..255
+    const int ep_tid = split ? ((threadIdx.x - 64) & 127) : (threadIdx.x - 64);   // index within the (group's) epilogue threads
+    const int lstep = split ? 2 : 1;              // tiles between two iterations of this warp
     const int row = q * 32 + lane;
     const int brick = p.BW * p.BH;
     const int groups = p.BN >> 6;
@@ -464,11 +543,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     struct RowGeo { int kt, wi, hi, ni, n, oh, ow; bool valid; long long pix, opix; };
     const int row_bn = row / brick, row_rem = row - row_bn * brick;
     const int row_bh = row_rem / p.BW, row_bw = row_rem - row_bh * p.BW;
-    auto geometry = [&](int tile) {
+    // Tile coordinates (kt, wi, hi, ni) advance by the mixed-radix digits of gridDim.x: no divisions per tile (the
+    // epilogue of the 64-channel layers is bound by its per-tile instruction count: ncu counted ~580 warp instructions
+    // per tile and warp, five integer divisions among them, for 32 values per thread)
+    int step_k, step_w, step_h, step_n;
+    {
+      int t = (int)gridDim.x;
+      step_k = t % p.tiles_k; t /= p.tiles_k;
+      step_w = t % p.tiles_w; t /= p.tiles_w;
+      step_h = t % p.tiles_h; step_n = t / p.tiles_h;
+    }
+    struct TilePos { int kt, wi, hi, ni; };
+    auto advance = [&](TilePos& t) {
+      t.kt += step_k;
+      int c = t.kt >= p.tiles_k ? 1 : 0;
+      t.kt -= c ? p.tiles_k : 0;
+      t.wi += step_w + c;
+      c = t.wi >= p.tiles_w ? 1 : 0;
+      t.wi -= c ? p.tiles_w : 0;
+      t.hi += step_h + c;
+      c = t.hi >= p.tiles_h ? 1 : 0;
+      t.hi -= c ? p.tiles_h : 0;
+      t.ni += step_n + c;
+    };
+    auto geometry = [&](const TilePos& t) {
       RowGeo g;
-      g.kt = tile % p.tiles_k;
-      const int mt = tile / p.tiles_k;
-      g.wi = mt % p.tiles_w; g.hi = (mt / p.tiles_w) % p.tiles_h; g.ni = mt / (p.tiles_w * p.tiles_h);
+      g.kt = t.kt; g.wi = t.wi; g.hi = t.hi; g.ni = t.ni;
       g.n = g.ni * p.BNI + row_bn; g.oh = g.hi * p.BH + row_bh; g.ow = g.wi * p.BW + row_bw;
       const int sh = g.oh * p.out_stride_sp + p.out_off_h, sw = g.ow * p.out_stride_sp + p.out_off_w;
       g.valid = (row_bn < p.BNI) && (g.n < p.N) && (g.oh < p.Ho) && (g.ow < p.Wo) && (sh < p.out_H) && (sw < p.out_W);
@@ -494,11 +594,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     };
-    RowGeo geo = geometry(blockIdx.x < total_tiles ? blockIdx.x : 0);
+    TilePos pos;
+    const long long first_tile = (long long)blockIdx.x + (long long)grp * gridDim.x;
+    {
+      int t = first_tile < total_tiles ? (int)first_tile : 0;
+      pos.kt = t % p.tiles_k; t /= p.tiles_k;
+      pos.wi = t % p.tiles_w; t /= p.tiles_w;
+      pos.hi = t % p.tiles_h; pos.ni = t / p.tiles_h;
+    }
+    RowGeo geo = geometry(pos);
     float mv[9];
     load_mask(geo, mv);
-    int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    int local = grp, sset_idx = grp;              // staging set: local % nsets (a group keeps to its own sets)
+    for (long long tile = first_tile; tile < total_tiles; tile += (long long)lstep * gridDim.x, local += lstep) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int kt = geo.kt, wi = geo.wi, hi = geo.hi, ni = geo.ni;
@@ -533,9 +641,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       {                                                           // next tile: geometry now, mask loads in flight
-        const int nt = tile + (int)gridDim.x;
-        geo = geometry(nt < total_tiles ? nt : tile);
-        if (nt < total_tiles) load_mask(geo, mv);
+        const long long nt = tile + (long long)lstep * gridDim.x;
+        if (nt < total_tiles) {
+          advance(pos);
+          if (split) advance(pos);
+          geo = geometry(pos);
+          load_mask(geo, mv);
+        }
       }
       mbar_wait(&bars->tfull[acc], acc_phase);
       tc_fence_after();
@@ -551,13 +663,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ---- smem-staged epilogue: the whole tile goes to `groups` swizzled 16 KB staging buffers
         //      (one per 64 output channels), then one thread issues the TMA stores; the staged
         //      (rounded) values also feed the per-channel BatchNorm partial sums.
-        uint8_t* sset = staging + (size_t)((local % nsets) * groups) * kABytes;
-        if (ep_tid == 0) {                       // the stores issued `nsets` tiles ago have drained this set
-          if (nsets >= 4) bulk_wait_read<3>();
-          else if (nsets == 2) bulk_wait_read<1>();
+        uint8_t* sset = staging + (size_t)(sset_idx * groups) * kABytes;
+        sset_idx += lstep;
+        if (sset_idx >= nsets) sset_idx = grp;
+        if (ep_tid == 0) {                       // the stores this thread issued (nsets / lstep) tiles ago have drained this set
+          const int mine = nsets / lstep;        // staging sets this issuing thread cycles through
+          if (mine >= 4) bulk_wait_read<3>();
+          else if (mine == 2) bulk_wait_read<1>();
           else bulk_wait_read<0>();
         }
-        epi_barrier();
+        if constexpr (split) epi_barrier_group(grp); else epi_barrier();
         // software-pipelined TMEM reads: the loads of group g+1 are in flight while group g is converted.
         // The epilogue is instruction-issue bound on the shallow layers (8 warps on 4 schedulers), so the
         // conversion uses packed fp32x2 multiplies and skips the multiply when there is no row scale.
@@ -573,7 +688,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // convert one 32-column half-group held in registers and store it to its swizzled staging rows (explicit
         // shared-space stores; the register arrays are indexed statically -- round 1's `(g & 1) ? vb : va` selection
         // cost one SEL per value and group, 20 % of the kernel's instructions in ncu)
-        auto convert_store = [&](const uint32_t (&v)[32], int g) {
+        auto convert_store = [&](const uint32_t (&v)[32], int step) {
+          const int g = split ? step >> 1 : step, half = split ? step & 1 : (warp - 2) >> 2;
           const uint32_t sbuf = sset_a + (uint32_t)g * kABytes + row_off;
 #pragma unroll
           for (int j2 = 0; j2 < 4; ++j2) {
@@ -589,24 +705,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             sts128(sbuf + ((((uint32_t)(half * 4 + j2)) ^ swz) << 4), w[0], w[1], w[2], w[3]);
           }
         };
-        auto load_group = [&](uint32_t (&v)[32], int g) {
-          tmem_ld16(taddr + g * 64 + half * 32, v);
-          tmem_ld16(taddr + g * 64 + half * 32 + 16, v + 16);
+        auto load_group = [&](uint32_t (&v)[32], int step) {       // split: step = 2 * group + half = 32-column block
+          const uint32_t col = split ? (uint32_t)step * 32u : (uint32_t)(step * 64 + half * 32);
+          tmem_ld16(taddr + col, v);
+          tmem_ld16(taddr + col + 16, v + 16);
         };
+        const int nsteps = split ? 2 * groups : groups;
         // software-pipelined TMEM reads, fully unrolled over the (at most four) 64-column groups: the loads of
         // group g + 1 are in flight while group g is converted
         uint32_t va[32], vb[32];
         load_group(va, 0);
 #pragma unroll
         for (int g2 = 0; g2 < 4; g2 += 2) {
-          if (g2 < groups) {
+          if (g2 < nsteps) {
             tmem_ld_wait();
-            if (g2 + 1 < groups) load_group(vb, g2 + 1);
+            if (g2 + 1 < nsteps) load_group(vb, g2 + 1);
             convert_store(va, g2);
           }
-          if (g2 + 1 < groups) {
+          if (g2 + 1 < nsteps) {
             tmem_ld_wait();
-            if (g2 + 2 < groups) load_group(va, g2 + 2);
+            if (g2 + 2 < nsteps) load_group(va, g2 + 2);
             convert_store(vb, g2 + 1);
           }
         }
@@ -614,7 +732,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->tempty[acc]);
         fence_async_smem();
-        epi_barrier();
+        if constexpr (split) epi_barrier_group(grp); else epi_barrier();
         if (ep_tid == 0 && !(p.debug & 2)) {
           for (int g = 0; g < groups; ++g) {
             if (p.accumulate)
@@ -635,6 +753,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int chunk = ep_tid & 7, ghalf = (ep_tid >> 3) & 1, rsub = ep_tid >> 4;        // rsub 0..15
           const int nrows = min(brick * p.BNI, kTileM);
           const uint32_t off = (uint32_t)rsub * 128u + (uint32_t)((chunk ^ (rsub & 7)) << 4);   // (rsub + 16 i) & 7 == rsub & 7
+          if (split) {
+            // four-warp group: thread (chunk, rsub) owns 8 channels of every 64-channel group (at most two here) and
+            // rows rsub, rsub + 16, ...
+            const int rs = ep_tid >> 3;                                                       // 0..15
+            const uint32_t off4 = (uint32_t)rs * 128u + (uint32_t)((chunk ^ (rs & 7)) << 4);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (k < groups) {
+                const uint32_t sbuf = sset_a + (uint32_t)k * kABytes + off4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                  if (rs + 16 * i < nrows) u = lds128(sbuf + i * 2048);
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const uint64_t t = bf16x2_to_f32x2(w[e]);
+                    st_sum[k][e] = add2(st_sum[k][e], t);
+                    st_sq[k][e] = fma2(t, t, st_sq[k][e]);
+                  }
+                }
+              }
+            }
+          } else if (groups == 1) {
+            // one 64-channel group: both half-warps work on it, rows rsub + 16 i with i in [4 ghalf, 4 ghalf + 4)
+            // (combined by the extra shuffle at the end)
+            const uint32_t sbuf = sset_a + off + (uint32_t)ghalf * 4u * 2048u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u = make_uint4(0u, 0u, 0u, 0u);
+              if (rsub + 16 * (i + 4 * ghalf) < nrows) u = lds128(sbuf + i * 2048);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint64_t t = bf16x2_to_f32x2(w[e]);
+                st_sum[0][e] = add2(st_sum[0][e], t);
+                st_sq[0][e] = fma2(t, t, st_sq[0][e]);
+              }
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const int g = ghalf + 2 * k;
@@ -689,7 +847,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tempty[acc]);
     }
-    if (p.tma_store && threadIdx.x == 64) bulk_wait_read<0>();     // staging must outlive the last store
+    if (p.tma_store && ep_tid == 0) bulk_wait_read<0>();           // staging must outlive the last store(s)
     if (p.bn_sums) {
       // lanes l and l ^ 16 hold the same channels (rows rsub and rsub ^ 1): combine, then the low half-warp
       // writes this warp's partial; the 8 warp partials are summed in a fixed order below (deterministic)
@@ -708,8 +866,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           su[e] += __shfl_xor_sync(0xffffffffu, su[e], 16);
           sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
         }
-        const int g = ghalf + 2 * k;
-        if (lane < 16 && g < groups) {
+        if (groups == 1 || split) {               // lanes l and l ^ 8 shared a channel group as well
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            su[e] += __shfl_xor_sync(0xffffffffu, su[e], 8);
+            sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 8);
+          }
+        }
+        const int g = split ? k : ghalf + 2 * k;
+        if ((split ? lane < 8 : lane < 16) && g < groups) {
           const int ch0 = g * 64 + chunk * 8;
 #pragma unroll
           for (int e = 0; e < 8; ++e) { mine[ch0 + e] = su[e]; mine[p.BN + ch0 + e] = sq[e]; }
@@ -1142,6 +1307,24 @@ int make_vw_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp, int Wo,
   return B2_OK;
 }
 
+// Row-stem map over the same zero-bordered input: plain (unswizzled) rows in 256-byte units -- dims (128 elements,
+// units per padded row, padded row, image), box (128, 9, 7, 1) = the seven input rows of one 128-pixel output-row tile,
+// 2304 B each (the last unit of a row runs into the next row: never read by the MMAs; the buffer has 256 B of slack)
+int make_vw_rows_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp) {
+  EncodeTiledFn fn = encode_fn();
+  B2_REQUIRE(fn != nullptr, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {128, (cuuint64_t)((Wp * 8 + 255) / 256), (cuuint64_t)Hp, (cuuint64_t)N};
+  cuuint64_t strides[3] = {256, (cuuint64_t)Wp * 8, (cuuint64_t)Hp * Wp * 8};
+  cuuint32_t box[4] = {128, kVwRowChunks, 7, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2_REQUIRE(r == CUDA_SUCCESS, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled(stem row map N=%d Hp=%d Wp=%d) failed: %d", N,
+             Hp, Wp, (int)r);
+  return B2_OK;
+}
+
 // 2-D map over a [rows, cols] bf16 matrix, box (64, box_rows)
 int make_mat_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows, int box_cols = 64) {
   EncodeTiledFn fn = encode_fn();
@@ -1206,6 +1389,7 @@ struct RunArgs {
   int vw_hp, vw_wp;                                            // != 0: `act` is a window-map stem input (make_vw_map)
   int b_mn;                                                    // filt is the UNtransposed filter [C][R*S*K] (dgrad, see FpropParams)
   int k32;                                                     // 32-element k-blocks, 64-byte swizzle (window-map stems)
+  int vw_rows;                                                 // row stems (FpropParams::vw_rows); filt as for k32
   int accumulate;                                              // dgrad: reduce-add into `out`
   float* bn_sums; bool* stats_fused; int bn_totals;           // optional fused BatchNorm statistics
   int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
@@ -1226,14 +1410,17 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.N = a.N; p.H = a.H; p.W = a.W; p.C = a.C; p.K = a.K; p.R = a.R; p.S = a.S;
   p.stride = a.stride; p.pad = a.pad; p.dil = a.dil; p.Ho = a.Ho; p.Wo = a.Wo;
   choose_brick(a.N, a.Ho, a.Wo, kTileM, 1, &p.BW, &p.BH, &p.BNI);
+  p.vw_rows = a.vw_rows;
+  if (a.vw_rows) { p.BW = kTileM; p.BH = 1; p.BNI = 1; }          // 128 pixels of one output row
   p.tiles_w = (a.Wo + p.BW - 1) / p.BW; p.tiles_h = (a.Ho + p.BH - 1) / p.BH; p.tiles_n = (a.N + p.BNI - 1) / p.BNI;
   p.BN = choose_bn(a.K);
   p.tiles_k = (a.K + p.BN - 1) / p.BN;
-  const int kbe = a.k32 ? 32 : kBlockK;
+  const int kbe = (a.k32 || a.vw_rows) ? 32 : kBlockK;
   p.k32 = a.k32;
   p.cblocks = (a.C + kbe - 1) / kbe;               // a ragged last block is zero-filled by TMA on the A side
   p.kblocks = a.R * a.S * p.cblocks;
-  const int a_stage_bytes = kTileM * kbe * 2;
+  const int a_stage_bytes = a.vw_rows ? (int)kABytes : kTileM * kbe * 2;
+  static_assert(7 * kVwRowPitch <= kABytes, "the seven raw stem rows must fit one ring stage");
   int stage_bytes = a_stage_bytes + p.BN * kbe * 2;
   static const bool no_tma_store = getenv("B2POSE_TC_NO_TMA_STORE") != nullptr;      // tuning switches
   static const bool no_fused_stats = getenv("B2POSE_TC_NO_FUSED_STATS") != nullptr;
@@ -1263,11 +1450,20 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   const int filt_bytes = p.kblocks * p.BN * kbe * 2;
   p.b_resident = (allow_resident && p.tiles_k == 1 && filt_bytes <= 96 * 1024 &&
                   (long long)p.tiles_w * p.tiles_h * p.tiles_n >= 2LL * b2_num_sms()) ? 1 : 0;
+  if (a.vw_rows) {
+    B2_REQUIRE(p.tiles_k == 1 && filt_bytes <= 96 * 1024 && a.R == 7 && a.S == 1 && a.C == 32 && !a.b_mn, B2_E_UNSUPPORTED,
+               "conv_tc: the row-stem mode needs a resident window filter [K <= 256][7][32]");
+    p.b_resident = 1;
+  }
   if (p.b_resident) {
     stage_bytes = a_stage_bytes;
     extra += filt_bytes;
     if (p.BN <= 64) p.n_staging = 2;           // two sets of one buffer: room for two more activation stages
   }
+  // narrow tiles: two four-warp epilogue groups on alternate tiles (needs one staging set per group)
+  static const bool allow_split = !(getenv("B2POSE_TC_EPI_SPLIT") && atoi(getenv("B2POSE_TC_EPI_SPLIT")) == 0);
+  p.epi_split = (allow_split && p.tma_store && p.BN <= 128 && p.n_staging / (p.BN / 64) >= 2 &&
+                 (p.n_staging / (p.BN / 64)) % 2 == 0) ? 1 : 0;
   extra += p.tma_store ? p.n_staging * (int)kABytes : 0;
   int stages = (smem_limit() - 2048 - (int)sizeof(PipeBars) - extra) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -1284,8 +1480,9 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.stride_w = a.vw_hp ? 1 : a.stride;
   CUtensorMap ma, mb, mo;
   B2_REQUIRE(!a.k32 || (a.vw_hp && !a.b_mn), B2_E_UNSUPPORTED, "conv_tc: 32-element k-blocks are a window-map stem mode");
-  int rc = a.vw_hp ? make_vw_map(&ma, a.act, a.N, a.vw_hp, a.vw_wp, a.Wo, p.BW, p.BH, p.BNI, kbe)
-                   : make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
+  int rc = a.vw_rows ? make_vw_rows_map(&ma, a.act, a.N, a.vw_hp, a.vw_wp)
+           : a.vw_hp ? make_vw_map(&ma, a.act, a.N, a.vw_hp, a.vw_wp, a.Wo, p.BW, p.BH, p.BNI, kbe)
+                     : make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
   if (rc) return rc;
   rc = p.b_mn ? make_mat_map(&mb, a.filt, a.C, (long long)a.R * a.S * a.K, 64)
               : make_mat_map(&mb, a.filt, a.K, (long long)a.R * a.S * a.C, p.BN, kbe);
@@ -1299,14 +1496,17 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024 + 16 + extra;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit());
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit());
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit());
     B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     configured = smem_limit();
   }
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_k;
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
   if (p.bn_sums && p.tiles_k > 1) grid = grid / p.tiles_k * p.tiles_k;      // fixed channel tile per CTA
-  cudaError_t le = launch_pdl(conv_tc_kernel, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, mo, p);
+  cudaError_t le = p.epi_split ? launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, mo, p)
+                               : launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, mo, p);
   B2_REQUIRE(le == cudaSuccess, B2_E_LAUNCH, "conv_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   B2_LAUNCH_CHECK("conv_tc_kernel");
   return B2_OK;
@@ -1342,7 +1542,13 @@ inline bool vw_fprop_k32() {
 }
 inline int vw_hp(const B2ConvDesc* d) { return d->H + 6; }
 inline int vw_wp(const B2ConvDesc* d) { return (d->W + 17) / 2 * 2; }      // even (16-byte row pitch), >= W + 16
-inline size_t vw_view_bytes(const B2ConvDesc* d) { return (size_t)d->N * vw_hp(d) * vw_wp(d) * 8; }
+inline size_t vw_view_bytes(const B2ConvDesc* d) { return (size_t)d->N * vw_hp(d) * vw_wp(d) * 8 + 256; }   // + row-map slack
+// fprop reads whole raw rows and windows them with overlapping no-swizzle descriptors (FpropParams::vw_rows);
+// B2POSE_STEM_ROWS=0 selects the window tensor map (TMA gathers one 64-byte window per output pixel)
+inline bool vw_fprop_rows() {
+  static const bool off = getenv("B2POSE_STEM_ROWS") && atoi(getenv("B2POSE_STEM_ROWS")) == 0;
+  return !off;
+}
 inline int stem_kpad(const B2ConvDesc* d) { return (d->R * d->S * d->C + 7) / 8 * 8; }
 
 int launch_vw_pad(const B2ConvDesc* d, const void* x, const float* mask, bf16* xp, cudaStream_t st) {
@@ -1425,10 +1631,11 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
     // B2_CONV_X_PREMASKED: the caller's x is zero wherever the mask is (network stems: veil = depth != 0)
     int rc = launch_vw_pad(d, x, (partial && !premasked) ? mask_in : nullptr, xp, st);
     if (rc) return rc;
-    const int win = vw_fprop_k32() ? 32 : 64;
+    const bool rows = vw_fprop_rows() && d->K <= 256;
+    const int win = (rows || vw_fprop_k32()) ? 32 : 64;
     vw_filter_kernel<<<(d->K * 7 * win + 255) / 256, 256, 0, st>>>((const bf16*)w, wk, d->K, d->C, win);
     B2_LAUNCH_CHECK("vw_filter");
-    a.act = xp; a.vw_hp = vw_hp(d); a.vw_wp = vw_wp(d); a.k32 = win == 32;
+    a.act = xp; a.vw_hp = vw_hp(d); a.vw_wp = vw_wp(d); a.k32 = !rows && win == 32; a.vw_rows = rows;
     a.H = vw_hp(d); a.W = d->Wo; a.C = win; a.filt = wk; a.R = 7; a.S = 1; a.stride = 2; a.pad = 0; a.dil = 1;
     a.pad_w = 0; a.use_pad_w = 1;
     if (partial) {

@@ -35,6 +35,10 @@ CASES = [
     ("c_tail",        2, 72,   80,  12, 12, 3, 1, 1, 1, False, False, False),
     ("stem_rgb_odd",  2, 3,    64,  65, 65, 7, 2, 3, 1, False, False, False),
     ("stem_c4",       1, 4,    64,  32, 32, 7, 2, 3, 1, False, False, False),
+    # stems at widths that fill / exceed / straddle the 128-pixel output-row tiles of the row-stem kernel
+    ("stem_depth_256", 2, 1,   64,  256, 256, 7, 2, 3, 1, True,  True,  False),
+    ("stem_rgb_wide", 1, 3,    64,  38, 300, 7, 2, 3, 1, False, False, False),
+    ("stem_pc_257",   1, 1,    64,  41, 257, 7, 2, 3, 1, True,  False, False),
     ("smallc_5x5",    2, 3,    32,  20, 20, 5, 1, 2, 1, False, False, False),
     # halo-tile mode (3x3 stride 1, Ho % 16 == 0, Wo % 8 == 0): several tiles per image, two channel blocks
     ("halo_48x40",    3, 128,  64,  48, 40, 3, 1, 1, 1, False, False, False),
