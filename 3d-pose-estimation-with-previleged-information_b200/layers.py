@@ -36,10 +36,17 @@ class _B2ConvBase(nn.Conv2d):
         self.weight.data = self.weight.data.contiguous(memory_format=torch.channels_last)
         self._shadow = None           # bf16 KRSC copy maintained by the Trainer's fused Adam step
         self._grad_sink = None        # [K,C,R,S] view of the Trainer's flat gradient buffer
+        self._bias_sink = None        # [K] view of the same buffer (layers with a bias)
 
     def shadow(self, dtype):
         s = self._shadow
         return s if (s is not None and s.dtype == dtype and dtype != self.weight.dtype) else None
+
+    def _sinks(self):
+        """(dw sink, db sink) inside a Trainer-managed model with gradients enabled, else None."""
+        if self._grad_sink is None or not torch.is_grad_enabled() or (self.bias is not None and self._bias_sink is None):
+            return None
+        return (self._grad_sink, self._bias_sink)
 
     def _conv_cfg(self, partial, premasked=False):
         return (self._s, self._p, self._d, partial, premasked, self.force_ffma)
@@ -58,7 +65,8 @@ class Conv2d(_B2ConvBase):
         return y.permute(0, 3, 1, 2)
 
     def forward_nhwc(self, x):
-        y, _ = ops.ConvFn.apply(x, None, self.weight, self.bias, self.shadow(x.dtype), self._conv_cfg(False))
+        y, _ = ops.ConvFn.apply(x, None, self.weight, self.bias, self.shadow(x.dtype), self._conv_cfg(False),
+                                self._sinks())
         return y
 
 
@@ -89,7 +97,7 @@ class PartialConv(_B2ConvBase):
 
     def forward_nhwc(self, x, mask, premasked=False):
         return ops.ConvFn.apply(x, mask, self.weight, self.bias, self.shadow(x.dtype),
-                                self._conv_cfg(True, premasked))
+                                self._conv_cfg(True, premasked), self._sinks())
 
 
 PartialConv2d = PartialConv     # the name BASELINE.json uses

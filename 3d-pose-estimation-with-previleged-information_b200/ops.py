@@ -366,9 +366,13 @@ class ConvFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, mask, weight, bias, shadow, cfg):
+    def forward(ctx, x, mask, weight, bias, shadow, cfg, sinks=None):
+        # sinks = (dw sink, db sink or None): views of the Trainer's flat gradient buffer that the kernels accumulate
+        # into directly (no zero-filled temporaries, no AccumulateGrad add) -- the regressor's 3x3 convolution
         stride, pad, dil, partial, premasked, force_ffma = cfg
+        ctx.sinks = sinks
         L.require_cuda(x, mask, weight, bias)
+        ctx.set_materialize_grads(False)             # no zero-filled gradient for the mask output
         x = x.contiguous()
         K, _, R, S = weight.shape
         flags = (L.CONV_PARTIAL if partial else 0) | (L.CONV_X_PREMASKED if premasked else 0) | \
@@ -400,7 +404,10 @@ class ConvFn(Function):
 
     @staticmethod
     def backward(ctx, dy, _dmask):
+        if dy is None:
+            return (None,) * 7
         x, mask, wk, ratio, mask_out = ctx.saved_tensors
+        sinks = ctx.sinks
         desc = ctx.desc
         dy = dy.contiguous()
         dx = dw = db = None
@@ -413,12 +420,17 @@ class ConvFn(Function):
                 if ctx.self_masked:
                     desc.flags |= L.CONV_X_PREMASKED
         if ctx.needs_input_grad[2]:
-            dw = _conv_wgrad(desc, x, mask, dy, ratio).to(ctx.wdtype)
+            if sinks is not None:
+                _conv_wgrad(desc, x, mask, dy, ratio, sink=sinks[0])          # accumulates into the flat buffer
+            else:
+                dw = _conv_wgrad(desc, x, mask, dy, ratio).to(ctx.wdtype)
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = torch.zeros(desc.K, dtype=torch.float32, device=dy.device)
+            to_sink = sinks is not None and sinks[1] is not None
+            acc = sinks[1] if to_sink else torch.zeros(desc.K, dtype=torch.float32, device=dy.device)
             rows = desc.N * desc.Ho * desc.Wo
-            L.call("b2_col_sum", L.ptr(dy), L.ptr(mask_out), L.ptr(db), rows, desc.K, L.dt(dy), L.stream())
-        return dx, None, dw, db, None, None
+            L.call("b2_col_sum", L.ptr(dy), L.ptr(mask_out), L.ptr(acc), rows, desc.K, L.dt(dy), L.stream())
+            db = None if to_sink else acc
+        return dx, None, dw, db, None, None, None
 
 
 class ConvBNFn(Function):
@@ -445,6 +457,9 @@ class ConvBNFn(Function):
         # its own dx there, with an event of its stream, instead of returning it.
         stride, pad, dil, partial, premasked, relu, mask_output, training, momentum, eps, force_ffma = cfg
         L.require_cuda(x, mask, weight, gamma)
+        # (without this, autograd hands backward a freshly zero-filled tensor for the unused mask gradient: one ATen
+        #  fill kernel per PartialConv layer and step)
+        ctx.set_materialize_grads(False)
         x = x.contiguous()
         K, _, R, S = weight.shape
         flags = (L.CONV_PARTIAL if partial else 0) | (L.CONV_X_PREMASKED if premasked else 0) | \
@@ -509,6 +524,8 @@ class ConvBNFn(Function):
 
     @staticmethod
     def backward(ctx, dz, _dmask):
+        if dz is None:                                   # nothing downstream used z
+            return (None,) * 14
         x, mask, wk, ratio, y, z, mean, invstd, gamma, beta, row_mask, gate = ctx.saved_tensors
         desc = ctx.desc
         dz = dz.contiguous()
@@ -587,6 +604,7 @@ class MaxPoolFn(Function):
     @staticmethod
     def forward(ctx, x, veil):
         L.require_cuda(x, veil)
+        ctx.set_materialize_grads(False)             # no zero-filled gradient for the pooled veil
         x = x.contiguous()
         N, H, W, Cc = x.shape
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
@@ -606,6 +624,8 @@ class MaxPoolFn(Function):
 
     @staticmethod
     def backward(ctx, dy, _dv):
+        if dy is None:
+            return None, None
         (arg,) = ctx.saved_tensors
         N, H, W, Cc = ctx.shape
         dy = dy.contiguous()

@@ -89,10 +89,12 @@ class _FlatState:
         self.v = torch.zeros_like(self.w)
         self.w16 = torch.zeros(total, dtype=torch.bfloat16, device=dev) if want_shadow else None
         self.params, self.offsets = params, offs
-        owner = {}
+        owner, bias_owner = {}, {}
         for mod in model.modules():
             if isinstance(mod, _B2ConvBase):
                 owner[id(mod.weight)] = mod
+                if mod.bias is not None:
+                    bias_owner[id(mod.bias)] = mod
         for p, o in zip(params, offs):
             n = p.numel()
             if p.dim() == 4:                       # filters: keep KRSC memory order
@@ -109,6 +111,8 @@ class _FlatState:
                 self.w[o:o + n].copy_(p.data.view(-1).float())
                 p.data = self.w[o:o + n].view(p.shape)
                 p.grad = self.g[o:o + n].view(p.shape)
+                if id(p) in bias_owner:
+                    bias_owner[id(p)]._bias_sink = p.grad
         if want_shadow:
             self.refresh_shadow()
 
