@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libb2pose.so")
 F32, BF16 = 0, 1
 CONV_PARTIAL, CONV_X_PREMASKED, CONV_DY_PRESCALED, CONV_FORCE_FFMA, CONV_DX_ACCUMULATE, CONV_BN_TOTALS, CONV_W_PREPARED = 1, 2, 4, 8, 16, 32, 64
 CONV_WS_HAS_COL = 128
-ABI_VERSION = 4
+CONV_X_CONCAT = 256
+ABI_VERSION = 5
 BN_PARTS = 320
 MIMIC_PARTS = 64
 
@@ -129,8 +130,21 @@ def call(name, *args):
             raise RuntimeError("libb2pose %s faulted%s: %s" % (name, desc, e)) from e
 
 
+class TensorPair:
+    """Two NHWC tensors standing for their channel concatenation (B2_CONV_X_CONCAT): passed to the C ABI as an array
+    of two device pointers."""
+
+    def __init__(self, a, b):
+        assert a.shape == b.shape and a.dtype == b.dtype and a.device == b.device
+        self.a, self.b = a, b
+        self.device, self.dtype = a.device, a.dtype
+        self._ptrs = (C.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+
+
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
+    """Device pointer of a tensor (None -> NULL; a TensorPair -> host array of its two device pointers)."""
+    if isinstance(t, TensorPair):
+        return t._ptrs
     return None if t is None else t.data_ptr()
 
 

@@ -68,6 +68,8 @@ extern "C" int b2_pconv_fprop(const B2ConvDesc* d, const void* x, const float* m
     B2_REQUIRE(ws_bytes >= conv_tc_workspace_bytes(d, 0), B2_E_WORKSPACE, "pconv_fprop: workspace too small");
     return conv_tc_fprop(d, x, mask_in, w, bias, y, mask_out, ratio_out, bn_sums, workspace, st);
   }
+  B2_REQUIRE(!(d->flags & B2_CONV_X_CONCAT), B2_E_UNSUPPORTED,
+             "pconv_fprop: B2_CONV_X_CONCAT needs the bf16 tensor-core path (plain stride-1 layer, C %% 128 == 0)");
   rc = conv_ffma_fprop(d, x, mask_in, w, bias, y, mask_out, ratio_out, st);
   if (rc) return rc;
   if (bn_sums && (d->flags & B2_CONV_BN_TOTALS))
@@ -90,6 +92,8 @@ extern "C" int b2_pconv_dgrad(const B2ConvDesc* d, const void* dy, const float* 
              "pconv_dgrad: B2_CONV_W_PREPARED needs the tensor-core path");
   B2_REQUIRE(!(d->flags & B2_CONV_DX_ACCUMULATE), B2_E_UNSUPPORTED,
              "pconv_dgrad: B2_CONV_DX_ACCUMULATE needs the bf16 tensor-core path (stride 1, C %% 64 == 0)");
+  B2_REQUIRE(!(d->flags & B2_CONV_X_CONCAT), B2_E_UNSUPPORTED,
+             "pconv_dgrad: B2_CONV_X_CONCAT needs the bf16 tensor-core path (plain stride-1 layer, C %% 128 == 0)");
   return conv_ffma_dgrad(d, dy, ratio, w, mask_in, dx, st);
 }
 
@@ -117,5 +121,7 @@ extern "C" int b2_pconv_wgrad(const B2ConvDesc* d, const void* x, const float* m
     B2_REQUIRE(ws_bytes >= conv_tc_workspace_bytes(d, 2), B2_E_WORKSPACE, "pconv_wgrad: workspace too small");
     return conv_tc_wgrad(d, x, mask_in, dy, ratio, dw, workspace, st);
   }
+  B2_REQUIRE(!(d->flags & B2_CONV_X_CONCAT), B2_E_UNSUPPORTED,
+             "pconv_wgrad: B2_CONV_X_CONCAT needs the bf16 tensor-core path (plain stride-1 layer, C %% 128 == 0)");
   return conv_ffma_wgrad(d, x, mask_in, dy, ratio, dw, st);
 }

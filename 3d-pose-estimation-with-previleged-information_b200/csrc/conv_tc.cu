@@ -312,6 +312,10 @@ struct FpropParams {
   int b_mn;                                            // dgrad straight from the untransposed filter W[k][tap][c]: B tiles are
                                                        // MN-major atoms [64 k][64 c], taps read in flipped order
   int n_staging;                                       // 16 KB output staging buffers of the TMA-store epilogue (<= kStaging)
+  int split_cb;                                        // B2_CONV_X_CONCAT fprop: channel blocks >= split_cb come from the
+                                                       // second input tensor (map_a2); 0 = one input tensor
+  int split_k;                                         // B2_CONV_X_CONCAT dgrad: output channels >= split_k go to the second
+                                                       // output tensor (map_out2); 0 = one output tensor
   int epi_split;                                       // the eight epilogue warps work as two groups of four on ALTERNATE
                                                        // tiles (group = TMEM accumulator buffer): two epilogue latency
                                                        // chains in flight instead of one (narrow tiles, BN <= 128)
@@ -344,7 +348,8 @@ struct __align__(8) PipeBars {
 template <bool kSplit>              // kSplit: FpropParams::epi_split, compiled in (a run-time switch cost the wide tiles 10-50 %)
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_out, const FpropParams p) {
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_a2,
+               const __grid_constant__ CUtensorMap map_out2, const FpropParams p) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms
@@ -373,6 +378,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     prefetch_map(&map_a);
     prefetch_map(&map_b);
     if (p.tma_store) prefetch_map(&map_out);
+    if (p.split_cb) prefetch_map(&map_a2);
+    if (p.split_k) prefetch_map(&map_out2);
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -421,6 +428,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t nphase = phase;
         if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        // channel concatenation of two inputs: the block comes from the tensor that holds it
+        const bool second = p.split_cb != 0 && cb >= p.split_cb;
+        const CUtensorMap* ma = second ? &map_a2 : &map_a;
+        const int ac0 = (second ? cb - p.split_cb : cb) * (int)kbe;
         if (p.debug & 24) {
           empty_ready = 0;
           if (lane == 0) {
@@ -428,7 +439,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               mbar_arrive(&bars->full[stage]);
             } else {                               // timing experiment: activation tile only (filter "resident")
               mbar_expect_tx(&bars->full[stage], a_box_bytes);
-              tma_load_4d(sa, &map_a, &bars->full[stage], cb * (int)kbe, iw0 + s * p.dil, ih0 + r * p.dil, n0);
+              tma_load_4d(sa, ma, &bars->full[stage], ac0, iw0 + s * p.dil, ih0 + r * p.dil, n0);
             }
           }
           __syncwarp();
@@ -436,7 +447,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const bool has_next = kb + 1 < ring_kblocks || more_tiles;
           const int mn_col = (p.R * p.S - 1 - (r * p.S + s)) * p.K + kt * p.BN;     // b_mn: flipped tap, first atom
           empty_ready = produce_fused((has_next ? 1u : 0u) | stage_flags, smem_u32(&bars->empty[nstage]), nphase ^ 1,
-                                      smem_u32(&bars->full[stage]), stage_tx, sa, &map_a, cb * (int)kbe,
+                                      smem_u32(&bars->full[stage]), stage_tx, sa, ma, ac0,
                                       iw0 + s * p.dil, ih0 + r * p.dil, n0, sa + a_bytes, &map_b,
                                       p.b_mn ? mn_col : bcol, p.b_mn ? cb * (int)kbe : kt * p.BN);
           if (p.b_mn && !p.b_resident && p.BN > 64) {
@@ -735,12 +746,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if constexpr (split) epi_barrier_group(grp); else epi_barrier();
         if (ep_tid == 0 && !(p.debug & 2)) {
           for (int g = 0; g < groups; ++g) {
+            int ch = kbase + g * 64;
+            const CUtensorMap* mo = &map_out;
+            if (p.split_k != 0 && ch >= p.split_k) { mo = &map_out2; ch -= p.split_k; }      // second half of a concatenation
             if (p.accumulate)
-              tma_reduce_add_4d(&map_out, smem_u32(sset + (size_t)g * kABytes), kbase + g * 64, wi * p.BW, hi * p.BH,
-                                ni * p.BNI);
+              tma_reduce_add_4d(mo, smem_u32(sset + (size_t)g * kABytes), ch, wi * p.BW, hi * p.BH, ni * p.BNI);
             else
-              tma_store_4d(&map_out, smem_u32(sset + (size_t)g * kABytes), kbase + g * 64, wi * p.BW, hi * p.BH,
-                           ni * p.BNI);
+              tma_store_4d(mo, smem_u32(sset + (size_t)g * kABytes), ch, wi * p.BW, hi * p.BH, ni * p.BNI);
           }
           bulk_commit();
         }
@@ -921,6 +933,7 @@ struct WgradParams {
   int T, tgroups;                  // filter taps per work item (they share the dY tile), ceil(taps/T)
   int bricks_per_split;
   int stages, tmem_cols;
+  int split_c;                     // B2_CONV_X_CONCAT: input channels >= split_c come from the second tensor (map_x2)
   float* dw;                       // [K][R*S][C] fp32
 };
 constexpr int kWgPix = 64;         // pixels per stage
@@ -929,7 +942,7 @@ constexpr int kWgPix = 64;         // pixels per stage
 // (one TMA fetch) and their own shifted X tile; their accumulators sit side by side in TMEM.
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
-                const WgradParams p) {
+                const __grid_constant__ CUtensorMap map_x2, const WgradParams p) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -950,6 +963,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     fence_barrier_init();
     prefetch_map(&map_dy);
     prefetch_map(&map_x);
+    if (p.split_c) prefetch_map(&map_x2);
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -992,15 +1006,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const int xw0 = ow0 * p.stride_w - p.pad_w, xh0 = oh0 * p.stride - p.pad;
         const bool has_next = b + 1 < b1 || more_items;
         // dy atoms: k channels [kt*128, +64) and [+64, +128); first x atom of the first tap
+        // (channel concatenation of two inputs: a channel tile lies in one of them, split_c % BNc == 0)
+        const bool second = p.split_c != 0 && ct * p.BNc >= p.split_c;
+        const CUtensorMap* mx = second ? &map_x2 : &map_x;
+        const int xc0 = ct * p.BNc - (second ? p.split_c : 0);
         empty_ready = produce_wgrad_fused(has_next ? 1u : 0u, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
                                           a_bytes + (uint32_t)nt * b_bytes, sa, &map_dy, kt * 128, ow0, oh0, n0,
-                                          sa + a_bytes, &map_x, ct * p.BNc, xw0 + s0 * p.dil, xh0 + r0 * p.dil);
+                                          sa + a_bytes, mx, xc0, xw0 + s0 * p.dil, xh0 + r0 * p.dil);
         if (nt * atoms > 1) {
           if (elect_one()) {
             int r = r0, s = s0;
             for (int j = 0; j < nt; ++j) {
               for (int a = (j == 0 ? 1 : 0); a < atoms; ++a)
-                tma_load_4d(sa + a_bytes + j * b_bytes + a * atom_bytes, &map_x, &bars->full[stage], ct * p.BNc + a * 64,
+                tma_load_4d(sa + a_bytes + j * b_bytes + a * atom_bytes, mx, &bars->full[stage], xc0 + a * 64,
                             xw0 + s * p.dil, xh0 + r * p.dil, n0);
               if (++s == p.S) { s = 0; ++r; }
             }
@@ -1390,6 +1408,8 @@ struct RunArgs {
   int b_mn;                                                    // filt is the UNtransposed filter [C][R*S*K] (dgrad, see FpropParams)
   int k32;                                                     // 32-element k-blocks, 64-byte swizzle (window-map stems)
   int vw_rows;                                                 // row stems (FpropParams::vw_rows); filt as for k32
+  const void* act2; int split_c;                               // B2_CONV_X_CONCAT fprop: channels >= split_c of `act` live in act2
+  void* out2; int split_k;                                     // B2_CONV_X_CONCAT dgrad: output channels >= split_k go to out2
   int accumulate;                                              // dgrad: reduce-add into `out`
   float* bn_sums; bool* stats_fused; int bn_totals;           // optional fused BatchNorm statistics
   int scale_mode; const float* mask_in; const float* row_scale; const float* bias;
@@ -1478,20 +1498,36 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   p.out_off_h = a.out_off_h; p.out_off_w = a.out_off_w;
   p.pad_w = a.use_pad_w ? a.pad_w : a.pad;
   p.stride_w = a.vw_hp ? 1 : a.stride;
-  CUtensorMap ma, mb, mo;
+  CUtensorMap ma, mb, mo, ma2, mo2;
+  p.split_cb = a.act2 ? a.split_c / kbe : 0;
+  p.split_k = a.out2 ? a.split_k : 0;
+  B2_REQUIRE(!a.act2 || (!a.vw_hp && a.split_c % kbe == 0 && a.split_c > 0 && a.split_c < a.C), B2_E_UNSUPPORTED,
+             "conv_tc: a concatenated input must split at a multiple of %d channels", kbe);
+  B2_REQUIRE(!a.out2 || (p.tma_store && a.split_k % 64 == 0 && a.split_k > 0 && a.split_k < a.K), B2_E_UNSUPPORTED,
+             "conv_tc: a concatenated output needs the TMA-store epilogue and a split at a multiple of 64 channels");
   B2_REQUIRE(!a.k32 || (a.vw_hp && !a.b_mn), B2_E_UNSUPPORTED, "conv_tc: 32-element k-blocks are a window-map stem mode");
   int rc = a.vw_rows ? make_vw_rows_map(&ma, a.act, a.N, a.vw_hp, a.vw_wp)
            : a.vw_hp ? make_vw_map(&ma, a.act, a.N, a.vw_hp, a.vw_wp, a.Wo, p.BW, p.BH, p.BNI, kbe)
-                     : make_act_map(&ma, a.act, a.N, a.H, a.W, a.C, p.BW, p.BH, p.BNI, a.stride);
+                     : make_act_map(&ma, a.act, a.N, a.H, a.W, a.act2 ? a.split_c : a.C, p.BW, p.BH, p.BNI, a.stride);
   if (rc) return rc;
+  ma2 = ma;
+  if (a.act2) {
+    rc = make_act_map(&ma2, a.act2, a.N, a.H, a.W, a.C - a.split_c, p.BW, p.BH, p.BNI, a.stride);
+    if (rc) return rc;
+  }
   rc = p.b_mn ? make_mat_map(&mb, a.filt, a.C, (long long)a.R * a.S * a.K, 64)
               : make_mat_map(&mb, a.filt, a.K, (long long)a.R * a.S * a.C, p.BN, kbe);
   if (rc) return rc;
   if (p.tma_store) {
-    rc = make_act_map(&mo, a.out, a.N, a.out_H, a.out_W, a.K, p.BW, p.BH, p.BNI, 1);
+    rc = make_act_map(&mo, a.out, a.N, a.out_H, a.out_W, a.out2 ? a.split_k : a.K, p.BW, p.BH, p.BNI, 1);
     if (rc) return rc;
   } else {
     mo = ma;
+  }
+  mo2 = mo;
+  if (a.out2) {
+    rc = make_act_map(&mo2, a.out2, a.N, a.out_H, a.out_W, a.K - a.split_k, p.BW, p.BH, p.BNI, 1);
+    if (rc) return rc;
   }
   const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024 + 16 + extra;
   static size_t configured = 0;
@@ -1505,8 +1541,9 @@ int run_conv_tc(const RunArgs& a, cudaStream_t st) {
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_k;
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
   if (p.bn_sums && p.tiles_k > 1) grid = grid / p.tiles_k * p.tiles_k;      // fixed channel tile per CTA
-  cudaError_t le = p.epi_split ? launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, mo, p)
-                               : launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, mo, p);
+  cudaError_t le = p.epi_split
+      ? launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, mo, ma2, mo2, p)
+      : launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, mo, ma2, mo2, p);
   B2_REQUIRE(le == cudaSuccess, B2_E_LAUNCH, "conv_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   B2_LAUNCH_CHECK("conv_tc_kernel");
   return B2_OK;
@@ -1575,10 +1612,20 @@ int launch_im2col(const B2ConvDesc* d, const void* x, const float* mask, bf16* c
 
 }  // namespace
 
+static bool dgrad_direct(const B2ConvDesc* d);
+static int wgrad_bnc(int C) { return C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64); }
+
 bool conv_tc_supported(const B2ConvDesc* d, int op) {
   if (!tc_enabled() || d->dtype != B2_BF16) return false;
   if (d->K % 8 != 0) return false;
   const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
+  if (d->flags & B2_CONV_X_CONCAT) {
+    // x (dx) = two tensors of C / 2 channels each: plain stride-1 layers whose halves are whole channel blocks
+    if (partial || is_stem(d) || d->stride != 1 || d->C % 128 != 0 || (d->flags & B2_CONV_DX_ACCUMULATE)) return false;
+    if (op == 1) return dgrad_direct(d) && (d->C / 2) % 64 == 0;
+    if (op == 2) return (d->C / 2) % wgrad_bnc(d->C) == 0;
+    return op == 0;
+  }
   if (is_stem(d)) return op == 0 || op == 2;                // im2col + GEMM; network inputs need no dgrad
   if (d->C % 8 != 0) return false;
   const bool one = (d->R == 1 && d->S == 1);
@@ -1624,6 +1671,11 @@ int conv_tc_fprop(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   const bool partial = d->flags & B2_CONV_PARTIAL, premasked = d->flags & B2_CONV_X_PREMASKED;
   const float* stem_ratio = nullptr;
   a.act = x; a.N = d->N; a.H = d->H; a.W = d->W; a.C = d->C;
+  if (d->flags & B2_CONV_X_CONCAT) {               // x = {first half, second half} of the channel concatenation
+    const void* const* xs = (const void* const*)x;
+    B2_REQUIRE(xs[0] && xs[1], B2_E_BADARG, "conv_tc_fprop: B2_CONV_X_CONCAT needs two input tensors");
+    a.act = xs[0]; a.act2 = xs[1]; a.split_c = d->C / 2;
+  }
   a.filt = w; a.K = d->K; a.R = d->R; a.S = d->S; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
   if (is_vw_stem(d)) {
     bf16* xp = (bf16*)workspace;
@@ -1723,8 +1775,14 @@ static int conv_tc_dgrad_impl(const B2ConvDesc* d, const void* dy, const float* 
     a.R = d->R; a.S = d->S; a.dil = d->dil; a.pad = d->dil * (d->R - 1) - d->pad;
     a.Ho = d->H; a.Wo = d->W; a.out_stride_sp = 1;
     a.accumulate = (d->flags & B2_CONV_DX_ACCUMULATE) ? 1 : 0;
+    if (d->flags & B2_CONV_X_CONCAT) {             // dx = {gradient of the first half, of the second half}
+      void* const* dxs = (void* const*)dx;
+      B2_REQUIRE(dxs[0] && dxs[1], B2_E_BADARG, "conv_tc_dgrad: B2_CONV_X_CONCAT needs two output tensors");
+      a.out = dxs[0]; a.out2 = dxs[1]; a.split_k = d->C / 2;
+    }
     return run_conv_tc(a, st);
   }
+  B2_REQUIRE(!(d->flags & B2_CONV_X_CONCAT), B2_E_UNSUPPORTED, "conv_tc_dgrad: B2_CONV_X_CONCAT needs the direct dgrad");
   if (d->stride == 1) {
     // dx = conv(dy, flipped/transposed filter), pad' = dil*(R-1) - pad
     TapMap tm;
@@ -1875,7 +1933,7 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
     }
   }
   p.tiles_w = (d->Wo + p.BW - 1) / p.BW; p.tiles_h = (d->Ho + p.BH - 1) / p.BH; p.tiles_n = (d->N + p.BNI - 1) / p.BNI;
-  p.BNc = d->C % 256 == 0 ? 256 : (d->C % 128 == 0 ? 128 : 64);
+  p.BNc = wgrad_bnc(d->C);
   p.ctiles = (d->C + p.BNc - 1) / p.BNc;
   p.ktiles = (d->K + 127) / 128;
   const int taps = d->R * d->S;
@@ -1911,12 +1969,25 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.T * p.BNc);
   p.dw = dw_out;
-  CUtensorMap mdy, mx;
+  CUtensorMap mdy, mx, mx2;
   int rc = make_act_map(&mdy, dys, d->N, d->Ho, d->Wo, d->K, p.BW, p.BH, p.BNI, 1);
   if (rc) return rc;
-  rc = vw ? make_vw_map(&mx, x, d->N, vw_hp(d0), vw_wp(d0), d->Wo, p.BW, p.BH, p.BNI)
-          : make_act_map(&mx, x, d->N, d->H, d->W, d->C, p.BW, p.BH, p.BNI, d->stride);
-  if (rc) return rc;
+  p.split_c = 0;
+  if (d0->flags & B2_CONV_X_CONCAT) {              // x = {first half, second half} of the channel concatenation
+    const void* const* xs = (const void* const*)x;
+    B2_REQUIRE(xs[0] && xs[1] && !vw && (d->C / 2) % p.BNc == 0, B2_E_UNSUPPORTED,
+               "conv_tc_wgrad: B2_CONV_X_CONCAT needs two inputs of a whole number of channel tiles");
+    p.split_c = d->C / 2;
+    rc = make_act_map(&mx, xs[0], d->N, d->H, d->W, d->C / 2, p.BW, p.BH, p.BNI, d->stride);
+    if (rc) return rc;
+    rc = make_act_map(&mx2, xs[1], d->N, d->H, d->W, d->C / 2, p.BW, p.BH, p.BNI, d->stride);
+    if (rc) return rc;
+  } else {
+    rc = vw ? make_vw_map(&mx, x, d->N, vw_hp(d0), vw_wp(d0), d->Wo, p.BW, p.BH, p.BNI)
+            : make_act_map(&mx, x, d->N, d->H, d->W, d->C, p.BW, p.BH, p.BNI, d->stride);
+    if (rc) return rc;
+    mx2 = mx;
+  }
   const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeBars) + 1024;
   static bool configured = false;
   if (!configured) {
@@ -1926,7 +1997,7 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   }
   const long long total = base_items * p.splits;
   int grid = (int)(total < b2_num_sms() ? total : b2_num_sms());
-  cudaError_t le = launch_pdl(wgrad_tc_kernel, dim3(grid), dim3(kThreads), smem, st, mdy, mx, p);
+  cudaError_t le = launch_pdl(wgrad_tc_kernel, dim3(grid), dim3(kThreads), smem, st, mdy, mx, mx2, p);
   B2_REQUIRE(le == cudaSuccess, B2_E_LAUNCH, "wgrad_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   B2_LAUNCH_CHECK("wgrad_tc_kernel");
   if (dwp && vw) {

@@ -119,8 +119,9 @@ class BatchNorm2d(nn.BatchNorm2d):
 
 
 def conv_bn(x, veil, conv, bn, relu, residual=None, mask_output=False, premasked=False, dx_holder=None,
-            res_holder=None, park_holder=None):
-    """conv -> bn (+residual) (+relu) (*veil) on NHWC tensors; returns (z, veil_out)."""
+            res_holder=None, park_holder=None, x2=None):
+    """conv -> bn (+residual) (+relu) (*veil) on NHWC tensors; returns (z, veil_out).
+    x2: convolve the channel concatenation [x, x2] without materialising it (ops.ConvBNFn)."""
     partial = isinstance(conv, PartialConv)
     training = bn.training
     if bn.momentum is None:
@@ -134,6 +135,6 @@ def conv_bn(x, veil, conv, bn, relu, residual=None, mask_output=False, premasked
         sinks = (conv._grad_sink,) + bn._grad_sinks
     z, vout = ops.ConvBNFn.apply(x, veil if partial else None, conv.weight, conv.shadow(x.dtype), bn.weight,
                                  bn.bias, bn.running_mean, bn.running_var, residual, cfg, sinks, dx_holder, res_holder,
-                                 park_holder)
+                                 park_holder, x2)
     bn.tick()
     return z, (vout if partial else veil)

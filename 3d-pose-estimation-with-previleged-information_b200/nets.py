@@ -131,7 +131,8 @@ class Fusion(nn.Module):
         self.bn = BatchNorm2d(inplanes)
 
     def forward_nhwc(self, x, y):
-        z, _ = conv_bn(torch.cat([x, y], dim=3), None, self.conv, self.bn, relu=True)
+        # the concatenation (fusionnet.py:137) is never materialised: the kernels read the two streams as they are
+        z, _ = conv_bn(x, None, self.conv, self.bn, relu=True, x2=y)
         return z
 
 

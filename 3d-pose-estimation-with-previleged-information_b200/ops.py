@@ -447,7 +447,10 @@ class ConvBNFn(Function):
 
     @staticmethod
     def forward(ctx, x, mask, weight, shadow, gamma, beta, running_mean, running_var, residual, cfg, sinks=None,
-                dx_holder=None, res_holder=None, park_holder=None):
+                dx_holder=None, res_holder=None, park_holder=None, x2=None):
+        # x2: the convolution runs over the channel concatenation [x, x2] (the fusion unit, fusionnet.py:137) without
+        # materialising it -- the tensor-core kernels read / write the two halves through two tensor maps
+        # (B2_CONV_X_CONCAT); where they cannot (fp32), the concatenation is formed here
         # dx_holder / res_holder: a dict shared by the first and the last conv+BN node of a residual
         # block with identity shortcut.  The last node parks the shortcut's gradient there instead of
         # returning it; the first node (whose backward always runs later) folds it into its dx with a
@@ -464,7 +467,19 @@ class ConvBNFn(Function):
         K, _, R, S = weight.shape
         flags = (L.CONV_PARTIAL if partial else 0) | (L.CONV_X_PREMASKED if premasked else 0) | \
                 (L.CONV_FORCE_FFMA if force_ffma else 0)
-        desc = make_desc(x.shape, K, R, S, stride, pad, dil, L.dt(x), flags)
+        ctx.concat = ctx.cat_split = None
+        if x2 is not None:
+            L.require_cuda(x2)
+            x2 = x2.contiguous()
+            full = tuple(x.shape[:3]) + (x.shape[3] + x2.shape[3],)
+            probe = make_desc(full, K, R, S, stride, pad, dil, L.dt(x), flags | L.CONV_X_CONCAT)
+            if x.shape == x2.shape and all(L.lib().b2_conv_uses_tensor_cores(C.byref(probe), op) for op in (0, 1, 2)):
+                flags |= L.CONV_X_CONCAT
+                ctx.concat = True
+            else:
+                ctx.cat_split = x.shape[3]
+                x, x2 = torch.cat([x, x2], dim=3), None
+        desc = make_desc(x.shape if x2 is None else full, K, R, S, stride, pad, dil, L.dt(x), flags)
         wk = filter_krsc(weight, x.dtype, shadow)
         if partial:
             mask = mask.contiguous()
@@ -485,8 +500,8 @@ class ConvBNFn(Function):
             # stem (im2col + GEMM): keep the workspace so that wgrad reuses the im2col matrix instead of rebuilding it
             nb = max(L.lib().b2_conv_workspace_bytes(C.byref(desc), 0), L.lib().b2_conv_workspace_bytes(C.byref(desc), 2))
             ctx.col_ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=x.device)
-        y, mask_out, ratio, sums = _conv_fprop(desc, x, mask if partial else None, wk, None, True, training, fast,
-                                               ctx.col_ws)
+        y, mask_out, ratio, sums = _conv_fprop(desc, x if x2 is None else L.TensorPair(x, x2),
+                                               mask if partial else None, wk, None, True, training, fast, ctx.col_ws)
         rows = desc.N * desc.Ho * desc.Wo
         z = torch.empty_like(y)
         mean = torch.empty(K, dtype=torch.float32, device=x.device)
@@ -517,7 +532,7 @@ class ConvBNFn(Function):
         # z is only needed for the ReLU gate of residual layers; otherwise the gate is recomputed from y
         ctx.save_for_backward(x, mask if partial else None, wk, ratio, y,
                               z if (relu and residual is not None and gate is None) else None,
-                              mean, invstd, gamma.detach(), beta.detach(), row_mask, gate)
+                              mean, invstd, gamma.detach(), beta.detach(), row_mask, gate, x2)
         if partial:
             ctx.mark_non_differentiable(mask_out)
         return z, mask_out
@@ -525,8 +540,8 @@ class ConvBNFn(Function):
     @staticmethod
     def backward(ctx, dz, _dmask):
         if dz is None:                                   # nothing downstream used z
-            return (None,) * 14
-        x, mask, wk, ratio, y, z, mean, invstd, gamma, beta, row_mask, gate = ctx.saved_tensors
+            return (None,) * 15
+        x, mask, wk, ratio, y, z, mean, invstd, gamma, beta, row_mask, gate, x2 = ctx.saved_tensors
         desc = ctx.desc
         dz = dz.contiguous()
         dev = dz.device
@@ -557,12 +572,20 @@ class ConvBNFn(Function):
                    L.ptr(dres), rows, K, L.dt(dz), L.stream())
         # dy now holds dRaw = dOut * ratio -> tell the conv kernels not to scale again
         desc.flags |= L.CONV_DY_PRESCALED
-        dx = dw = None
+        dx = dw = dx2 = None
         if ctx.needs_input_grad[2]:        # first: on the side stream it then runs beside this layer's dgrad
-            dw = _conv_wgrad(desc, x, mask, dy, None, sinks[0] if sinks is not None else None, ctx.col_ws)
+            dw = _conv_wgrad(desc, x if x2 is None else L.TensorPair(x, x2), mask, dy, None,
+                             sinks[0] if sinks is not None else None, ctx.col_ws)
             if dw is not None:
                 dw = dw.to(ctx.wdtype)
-        if ctx.needs_input_grad[0]:
+        if ctx.concat:
+            # gradient of the two halves of the (never materialised) concatenation, written by one dgrad launch
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[14]:
+                dx, dx2 = torch.empty_like(x), torch.empty_like(x2)
+                ws, wsn = workspace(L.lib().b2_conv_workspace_bytes(C.byref(desc), 1), dev)
+                L.call("b2_pconv_dgrad", C.byref(desc), L.ptr(dy), None, L.ptr(wk), None, L.ptr(L.TensorPair(dx, dx2)),
+                       L.ptr(ws), wsn, L.stream())
+        elif ctx.needs_input_grad[0]:
             addend = None
             if ctx.dx_holder is not None:
                 addend = ctx.dx_holder.pop("dres", None)
@@ -595,7 +618,9 @@ class ConvBNFn(Function):
             ev.record(torch.cuda.current_stream(dev))
             ctx.park_holder["dres"], ctx.park_holder["ev"] = dx, ev
             dx = None
-        return dx, None, dw, None, dgamma, dbeta, None, None, dres, None, None, None, None, None
+        if ctx.cat_split is not None and dx is not None:          # the concatenation was formed in forward (fp32 path)
+            dx, dx2 = dx[..., :ctx.cat_split], dx[..., ctx.cat_split:]
+        return dx, None, dw, None, dgamma, dbeta, None, None, dres, None, None, None, None, None, dx2
 
 
 class MaxPoolFn(Function):

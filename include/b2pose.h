@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 4
+#define B2_ABI_VERSION 5
 
 /* slots of a BatchNorm partial-sum buffer: float[B2_BN_PARTS][2*C] (see the BatchNorm section) */
 #define B2_BN_PARTS 320
@@ -55,8 +55,14 @@ enum {
                              /* to (totals BatchNorm path, needs b2_bn_totals_supported(K, dtype))  */
   B2_CONV_W_PREPARED = 64,   /* dgrad: `w` is the buffer b2_pconv_dgrad_filter produced for this     */
                              /* descriptor (flipped / transposed filter), not the KRSC filter        */
-  B2_CONV_WS_HAS_COL = 128   /* wgrad of a stem layer (C <= 4): `workspace` is the very buffer the   */
+  B2_CONV_WS_HAS_COL = 128,  /* wgrad of a stem layer (C <= 4): `workspace` is the very buffer the   */
                              /* fprop of the same descriptor ran with, its im2col matrix is reused    */
+  B2_CONV_X_CONCAT = 256     /* the input is the channel concatenation of TWO NHWC tensors of C / 2   */
+                             /* channels each (the fusion unit, fusionnet.py:137) that is never      */
+                             /* materialised: `x` (fprop, wgrad) is a const void* const[2], `dx`     */
+                             /* (dgrad) a void* const[2] of the two halves.  bf16 tensor-core path,  */
+                             /* plain stride-1 layers with C % 128 == 0 (b2_conv_uses_tensor_cores   */
+                             /* answers for the flagged descriptor); B2_E_UNSUPPORTED otherwise      */
 };
 
 typedef struct B2ConvDesc {

@@ -27,7 +27,7 @@ def test_library_exports_header(b2pose):
     for s in syms:
         assert hasattr(lib, s), "libb2pose.so does not export %s" % s
     assert sorted(b2pose._lib.SIGNATURES) == syms          # the binding covers exactly the header
-    assert b2pose._lib.lib().b2_abi_version() == b2pose._lib.ABI_VERSION == 4
+    assert b2pose._lib.lib().b2_abi_version() == b2pose._lib.ABI_VERSION == 5
 
 
 def test_header_arg_counts_match_binding(b2pose):

@@ -146,3 +146,38 @@ def test_dgrad_reduce_add(b2pose, dev):
     addend = torch.randn(2, 17, 17, 128, generator=gen).to(dev).bfloat16()
     got = b2pose.ops._conv_dgrad(desc, dy, None, w, None, addend.clone())
     assert rel_err(got, b2pose.ops._conv_dgrad(desc, dy, None, w, None) + addend) < 4e-3
+
+
+@pytest.mark.parametrize("cin,k,ksz,pad", [(512, 512, 1, 0), (256, 64, 3, 1)])
+def test_concat_input_matches_materialised_cat(b2pose, dev, cin, k, ksz, pad):
+    """B2_CONV_X_CONCAT (the fusion unit, fusionnet.py:137): conv + BN + ReLU over [x, x2] read through two tensor maps
+    must equal the same layer over torch.cat([x, x2]) -- output, both input gradients, filter and BatchNorm gradients."""
+    from b2pose.layers import conv_bn
+    gen = torch.Generator().manual_seed(31)
+    N, H, W = 3, 24, 20
+    conv = b2pose.Conv2d(2 * cin, k, kernel_size=ksz, padding=pad, bias=False).to(dev)
+    bn = b2pose.BatchNorm2d(k).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen) * (1.0 / (2 * cin * ksz * ksz)) ** 0.5)
+        bn.weight.copy_(torch.rand(k, generator=gen) + 0.5)
+        bn.bias.copy_(torch.randn(k, generator=gen) * 0.1)
+    a = torch.randn(N, H, W, cin, generator=gen).to(dev).bfloat16()
+    b = torch.randn(N, H, W, cin, generator=gen).to(dev).bfloat16()
+    cot = torch.randn(N, H, W, k, generator=gen).to(dev).bfloat16()
+    L = b2pose._lib
+    desc = b2pose.ops.make_desc((N, H, W, 2 * cin), k, ksz, ksz, 1, pad, 1, L.BF16, L.CONV_X_CONCAT)
+    assert all(L.lib().b2_conv_uses_tensor_cores(C.byref(desc), op) == 1 for op in (0, 1, 2))
+    outs = []
+    for split in (True, False):
+        conv.weight.grad = bn.weight.grad = bn.bias.grad = None
+        xa, xb = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        if split:
+            z, _ = conv_bn(xa, None, conv, bn, relu=True, x2=xb)
+        else:
+            z, _ = conv_bn(torch.cat([xa, xb], dim=3), None, conv, bn, relu=True)
+        (z.float() * cot.float()).sum().backward()
+        outs.append((z.detach(), xa.grad, xb.grad, conv.weight.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()))
+    for name, got, want in zip(("z", "dx", "dx2", "dw", "dgamma", "dbeta"), outs[0], outs[1]):
+        e = rel_err(got, want)
+        print("concat %dx%d k%d %s: %.2e" % (2 * cin, k, ksz, name, e))
+        assert e < 5e-3, (name, e)           # same MMAs; only the order of the fp32 atomics (statistics, dW) differs
