@@ -934,9 +934,15 @@ struct WgradParams {
   int bricks_per_split;
   int stages, tmem_cols;
   int split_c;                     // B2_CONV_X_CONCAT: input channels >= split_c come from the second tensor (map_x2)
+  int vw_rows;                     // row stems: a stage holds the brick's seven raw input rows [7][kVwgRowPitch]; the X
+                                   // operand of tap row r is an MN-major no-swizzle descriptor over row r (pixel p,
+                                   // window chunk c -> raw chunk p + c), 32 window elements per tap row; 1 / 2 selects
+                                   // which descriptor field carries which stride
   float* dw;                       // [K][R*S][C] fp32
 };
 constexpr int kWgPix = 64;         // pixels per stage
+constexpr uint32_t kVwgRowUnits = 5, kVwgRowPitch = kVwgRowUnits * 256;   // raw stem row of a 64-pixel brick: 67 x 16 B
+constexpr uint32_t kVwgRowsBytes = 9 * 1024;                              // seven of them, rounded to the swizzle atom
 
 // Work item = (pixel split, tap group, c-tile, k-tile).  All T taps of a group read the same dY tile
 // (one TMA fetch) and their own shifted X tile; their accumulators sit side by side in TMEM.
@@ -949,7 +955,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   // stage: A = dy [2 atoms of 64 k][64 pix][128 B]  (16 KB), B = T x ( x [BNc/64 atoms][64 pix][128 B] )
   const uint32_t atom_bytes = kWgPix * 128;
   const uint32_t a_bytes = 2 * atom_bytes, b_bytes = (uint32_t)(p.BNc / 64) * atom_bytes;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)p.T * b_bytes;
+  const uint32_t stage_bytes = a_bytes + (p.vw_rows ? kVwgRowsBytes : (uint32_t)p.T * b_bytes);
   PipeBars* bars = reinterpret_cast<PipeBars*>(smem + (size_t)p.stages * stage_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.R * p.S;
@@ -1010,6 +1016,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const bool second = p.split_c != 0 && ct * p.BNc >= p.split_c;
         const CUtensorMap* mx = second ? &map_x2 : &map_x;
         const int xc0 = ct * p.BNc - (second ? p.split_c : 0);
+        if (p.vw_rows)     // one box: the seven raw rows (256-byte units of the padded row, 64 pixels = 4 units)
+          empty_ready = produce_wgrad_fused(has_next ? 1u : 0u, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
+                                            a_bytes + 7u * kVwgRowPitch, sa, &map_dy, kt * 128, ow0, oh0, n0,
+                                            sa + a_bytes, &map_x, 0, ow0 >> 4, oh0 * 2);
+        else
         empty_ready = produce_wgrad_fused(has_next ? 1u : 0u, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
                                           a_bytes + (uint32_t)nt * b_bytes, sa, &map_dy, kt * 128, ow0, oh0, n0,
                                           sa + a_bytes, mx, xc0, xw0 + s0 * p.dil, xh0 + r0 * p.dil);
@@ -1069,10 +1080,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           uint32_t flags = 0, q1, q2;
           if (j == 0) flags |= ((!last || more_items) ? kPoll1 : 0u) | ((last && more_items) ? kPoll2 : 0u);
           if (j == nt - 1) flags |= kCommit1 | (last ? kCommit2 : 0u);
-          mma4_fused(tmem_d + (uint32_t)(j * p.BNc), adesc, smem_desc(sa + a_bytes + j * b_bytes, atom_bytes, 1024), 128ull,
+          // row stems: MN-major without swizzle -- window chunks 16 B apart along N, 8-pixel groups 128 B apart
+          // along K, 16 pixels (256 B) per MMA
+          const uint64_t bdesc = p.vw_rows
+              ? (p.vw_rows == 1 ? smem_desc_plain(sa + a_bytes + (uint32_t)j * kVwgRowPitch, 128, 16)
+                                : smem_desc_plain(sa + a_bytes + (uint32_t)j * kVwgRowPitch, 16, 128))
+              : smem_desc(sa + a_bytes + j * b_bytes, atom_bytes, 1024);
+          mma4_fused(tmem_d + (uint32_t)(j * p.BNc), adesc, bdesc, 128ull,
                      idesc, (uint32_t)(b - b0), flags, smem_u32(&bars->full[nstage]), nphase,
                      smem_u32(&bars->tempty[nacc]), nacc_parity, smem_u32(&bars->empty[stage]),
-                     smem_u32(&bars->tfull[acc]), q1, q2, 128ull);
+                     smem_u32(&bars->tfull[acc]), q1, q2, p.vw_rows ? 16ull : 128ull);
           if (j == 0) { r1 = q1; r2 = q2; }
         }
         full_ready = r1;
@@ -1245,12 +1262,12 @@ __global__ void vw_filter_kernel(const bf16* __restrict__ w, bf16* __restrict__ 
   }
 }
 // dw[k][r][s][c] += dWk[k][r][4 (s + 1) + c]
-__global__ void vw_unfilter_add_kernel(const float* __restrict__ dwk, float* __restrict__ dw, int K, int C) {
+__global__ void vw_unfilter_add_kernel(const float* __restrict__ dwk, float* __restrict__ dw, int K, int C, int win) {
   const int total = K * 49 * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % C, rs = (i / C) % 49, k = i / (C * 49);
     const int r = rs / 7, s2 = rs - r * 7;
-    dw[i] += dwk[((long long)k * 7 + r) * 64 + 4 * (s2 + 1) + c];
+    dw[i] += dwk[((long long)k * 7 + r) * win + 4 * (s2 + 1) + c];
   }
 }
 
@@ -1326,14 +1343,16 @@ int make_vw_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp, int Wo,
 }
 
 // Row-stem map over the same zero-bordered input: plain (unswizzled) rows in 256-byte units -- dims (128 elements,
-// units per padded row, padded row, image), box (128, 9, 7, 1) = the seven input rows of one 128-pixel output-row tile,
-// 2304 B each (the last unit of a row runs into the next row: never read by the MMAs; the buffer has 256 B of slack)
-int make_vw_rows_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp) {
+// units per padded row, padded row, image), box (128, units, 7, 1) = the seven input rows of one output-row tile (fprop:
+// 128 pixels, 9 units; wgrad: 64 pixels, 5 units).  Wp is a multiple of 32 pixels (vw_wp), so the units tile a row
+// exactly and the part of a box behind the end of its row is zero-filled
+int make_vw_rows_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp, uint32_t units = kVwRowChunks) {
   EncodeTiledFn fn = encode_fn();
   B2_REQUIRE(fn != nullptr, B2_E_LAUNCH, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[4] = {128, (cuuint64_t)((Wp * 8 + 255) / 256), (cuuint64_t)Hp, (cuuint64_t)N};
+  B2_REQUIRE(Wp % 32 == 0, B2_E_BADARG, "conv_tc: the stem row map needs a padded width that is a multiple of 32");
+  cuuint64_t dims[4] = {128, (cuuint64_t)(Wp / 32), (cuuint64_t)Hp, (cuuint64_t)N};
   cuuint64_t strides[3] = {256, (cuuint64_t)Wp * 8, (cuuint64_t)Hp * Wp * 8};
-  cuuint32_t box[4] = {128, kVwRowChunks, 7, 1};
+  cuuint32_t box[4] = {128, units, 7, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1578,10 +1597,18 @@ inline bool vw_fprop_k32() {
   return !win64;
 }
 inline int vw_hp(const B2ConvDesc* d) { return d->H + 6; }
-inline int vw_wp(const B2ConvDesc* d) { return (d->W + 17) / 2 * 2; }      // even (16-byte row pitch), >= W + 16
-inline size_t vw_view_bytes(const B2ConvDesc* d) { return (size_t)d->N * vw_hp(d) * vw_wp(d) * 8 + 256; }   // + row-map slack
+// >= W + 16 and a multiple of 32 pixels: a padded row is a whole number of the 256-byte units the row maps count in, so
+// whatever a box reads past the end of a row is zero-filled by TMA (never the next row, never memory behind the buffer)
+inline int vw_wp(const B2ConvDesc* d) { return (d->W + 16 + 31) / 32 * 32; }
+inline size_t vw_view_bytes(const B2ConvDesc* d) { return (size_t)d->N * vw_hp(d) * vw_wp(d) * 8; }
 // fprop reads whole raw rows and windows them with overlapping no-swizzle descriptors (FpropParams::vw_rows);
 // B2POSE_STEM_ROWS=0 selects the window tensor map (TMA gathers one 64-byte window per output pixel)
+// wgrad of the stems the same way (WgradParams::vw_rows); B2POSE_STEM_WGRAD_ROWS=0 -> window tensor map, =2 -> the
+// other assignment of the two descriptor strides (bring-up switch)
+inline int vw_wgrad_rows() {
+  static const int v = getenv("B2POSE_STEM_WGRAD_ROWS") ? atoi(getenv("B2POSE_STEM_WGRAD_ROWS")) : 1;
+  return v;
+}
 inline bool vw_fprop_rows() {
   static const bool off = getenv("B2POSE_STEM_ROWS") && atoi(getenv("B2POSE_STEM_ROWS")) == 0;
   return !off;
@@ -1876,6 +1903,7 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   float* dwp = nullptr;
   int kpad = 0;
   bool vw = false;
+  int vw_rows = 0;
   if (is_vw_stem(d)) {
     vw = true;
     bf16* xp = (bf16*)ws;
@@ -1889,7 +1917,8 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
     cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)d->K * 7 * 64 * 4, st);
     B2_REQUIRE(e == cudaSuccess, B2_E_LAUNCH, "conv_tc_wgrad: memset failed: %s", cudaGetErrorString(e));
     x = xp;
-    g.H = vw_hp(d); g.W = d->Wo; g.C = 64; g.R = 7; g.S = 1; g.stride = 2; g.pad = 0; g.dil = 1;
+    vw_rows = vw_wgrad_rows();
+    g.H = vw_hp(d); g.W = d->Wo; g.C = vw_rows ? 32 : 64; g.R = 7; g.S = 1; g.stride = 2; g.pad = 0; g.dil = 1;
     dw_out = dwp;
   } else if (is_stem(d)) {
     kpad = stem_kpad(d);
@@ -1932,12 +1961,15 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
       }
     }
   }
+  p.vw_rows = vw_rows;
+  if (vw_rows) { p.BW = kWgPix; p.BH = 1; p.BNI = 1; }          // 64 pixels of one output row
   p.tiles_w = (d->Wo + p.BW - 1) / p.BW; p.tiles_h = (d->Ho + p.BH - 1) / p.BH; p.tiles_n = (d->N + p.BNI - 1) / p.BNI;
-  p.BNc = wgrad_bnc(d->C);
+  p.BNc = vw_rows ? 32 : wgrad_bnc(d->C);
   p.ctiles = (d->C + p.BNc - 1) / p.BNc;
   p.ktiles = (d->K + 127) / 128;
   const int taps = d->R * d->S;
   p.T = 256 / p.BNc;                       // 2 accumulator sets x T x BNc <= 512 TMEM columns
+  if (vw_rows) p.T = 7;                    // (row stems: all seven tap rows share the dY tile, 2 x 7 x 32 columns)
   if (p.T > taps) p.T = taps;
   if (p.T < 1) p.T = 1;
   p.tgroups = (taps + p.T - 1) / p.T;
@@ -1957,7 +1989,7 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   if (want < 1) want = 1;
   p.bricks_per_split = (int)((bricks + want - 1) / want);
   p.splits = (int)((bricks + p.bricks_per_split - 1) / p.bricks_per_split);
-  const int stage_bytes = 2 * kWgPix * 128 + p.T * (p.BNc / 64) * kWgPix * 128;
+  const int stage_bytes = 2 * kWgPix * 128 + (vw_rows ? (int)kVwgRowsBytes : p.T * (p.BNc / 64) * kWgPix * 128);
   // B2POSE_WGRAD_SMEM_KB caps the ring so that blocks of other kernels (the BatchNorm streams running on the
   // main stream while wgrad runs on the side stream) can share the SM
   static const int env_kb = getenv("B2POSE_WGRAD_SMEM_KB") ? atoi(getenv("B2POSE_WGRAD_SMEM_KB")) : 0;
@@ -1983,8 +2015,9 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
     rc = make_act_map(&mx2, xs[1], d->N, d->H, d->W, d->C / 2, p.BW, p.BH, p.BNI, d->stride);
     if (rc) return rc;
   } else {
-    rc = vw ? make_vw_map(&mx, x, d->N, vw_hp(d0), vw_wp(d0), d->Wo, p.BW, p.BH, p.BNI)
-            : make_act_map(&mx, x, d->N, d->H, d->W, d->C, p.BW, p.BH, p.BNI, d->stride);
+    rc = vw_rows ? make_vw_rows_map(&mx, x, d->N, vw_hp(d0), vw_wp(d0), kVwgRowUnits)
+         : vw    ? make_vw_map(&mx, x, d->N, vw_hp(d0), vw_wp(d0), d->Wo, p.BW, p.BH, p.BNI)
+                 : make_act_map(&mx, x, d->N, d->H, d->W, d->C, p.BW, p.BH, p.BNI, d->stride);
     if (rc) return rc;
     mx2 = mx;
   }
@@ -2001,7 +2034,7 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   B2_REQUIRE(le == cudaSuccess, B2_E_LAUNCH, "wgrad_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   B2_LAUNCH_CHECK("wgrad_tc_kernel");
   if (dwp && vw) {
-    vw_unfilter_add_kernel<<<(d0->K * 49 * d0->C + 255) / 256, 256, 0, st>>>(dwp, dw, d0->K, d0->C);
+    vw_unfilter_add_kernel<<<(d0->K * 49 * d0->C + 255) / 256, 256, 0, st>>>(dwp, dw, d0->K, d0->C, vw_rows ? 32 : 64);
     B2_LAUNCH_CHECK("vw_unfilter_add");
   } else if (dwp) {
     const int rsc = d0->R * d0->S * d0->C;

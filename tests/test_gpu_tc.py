@@ -56,6 +56,11 @@ def _uses_tc(b2pose, x_shape, K, k, s, p, d, flags):
 def test_tc_conv(b2pose, dev, case):
     name, N, Cin, K, H, W, k, s, p, d, partial, premasked, bias = case
     L = b2pose._lib
+    # poison every scratch buffer (0xFF bytes are NaNs in bf16 and fp32): a kernel that reads workspace memory it did not
+    # write (a TMA box running past a padded row, an unwritten staging tile) must not get away with zeros
+    for ws in b2pose.ops._workspaces.values():
+        ws.fill_(0xFF)
+    torch.empty(64 << 20, dtype=torch.uint8, device=dev).fill_(0xFF)        # and what the allocator hands out next
     gen = torch.Generator().manual_seed(abs(hash(name)) % (1 << 31))
     bf = lambda t: t.bfloat16().float()
     w = bf(torch.randn(K, Cin, k, k, generator=gen) * (2.0 / (k * k * K)) ** 0.5)
