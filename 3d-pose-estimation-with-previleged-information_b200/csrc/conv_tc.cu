@@ -366,7 +366,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (p.bn_sums)      // [8 epilogue warps][2*BN]: warp-private partials, no shared atomics
     for (int i = threadIdx.x; i < 16 * p.BN; i += kConvThreads) s_stats[i] = 0.f;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role branches and everything
+  // computed inside them (ring counters, shared-memory addresses, MMA descriptors) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
   const int total_tiles = m_tiles * p.tiles_k;
 
@@ -385,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);      // (warp-uniform for the compiler, see `warp`)
   pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
 
   if (warp == 0) {
@@ -957,7 +959,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   const uint32_t a_bytes = 2 * atom_bytes, b_bytes = (uint32_t)(p.BNc / 64) * atom_bytes;
   const uint32_t stage_bytes = a_bytes + (p.vw_rows ? kVwgRowsBytes : (uint32_t)p.T * b_bytes);
   PipeBars* bars = reinterpret_cast<PipeBars*>(smem + (size_t)p.stages * stage_bytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role branches and everything
+  // computed inside them (ring counters, shared-memory addresses, MMA descriptors) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int taps = p.R * p.S;
   const int total_items = p.splits * p.tgroups * p.ctiles * p.ktiles;
   const int total_bricks = p.tiles_n * p.tiles_h * p.tiles_w;
@@ -975,7 +979,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);      // (warp-uniform for the compiler, see `warp`)
   pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
 
   // item decode: split fastest so CTAs running together share the same filter tile / spread pixels
