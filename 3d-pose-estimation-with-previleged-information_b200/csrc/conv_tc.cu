@@ -154,6 +154,33 @@ __device__ __forceinline__ void mma4_fused(uint32_t tmem_d, uint64_t adesc, uint
         "r"(poll1_parity), "r"(poll2_bar), "r"(poll2_parity), "r"(commit1_bar), "r"(commit2_bar), "l"(bstep)
       : "memory");
 }
+// The common case of mma4_fused with every switch fixed at compile time -- four MMAs, poll the next stage's `full`
+// barrier, commit to this stage's `empty` barrier: the flag decoding (ten uniform instructions) disappears from the issue
+// loop of all but a tile's last k-block.
+__device__ __forceinline__ void mma4_steady(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc0,
+                                            uint32_t poll_bar, uint32_t poll_parity, uint32_t commit_bar, uint32_t& ready,
+                                            uint64_t bstep) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pw, pe, pa;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%6], %7;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %5, 0;\n\t"
+      "add.s64 a1, %2, 2;\n\tadd.s64 a2, %2, 4;\n\tadd.s64 a3, %2, 6;\n\t"
+      "add.s64 b1, %3, %9;\n\tadd.s64 b2, b1, %9;\n\tadd.s64 b3, b2, %9;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, pa;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %4, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %4, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %4, 1;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "selp.u32 %0, 1, 0, pw;\n\t"
+      "}"
+      : "=r"(ready)
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc0), "r"(poll_bar), "r"(poll_parity), "r"(commit_bar),
+        "l"(bstep)
+      : "memory");
+}
 // Row stems: the fourteen MMAs of one tile (seven tap rows x two K = 16 steps) in ONE block -- the cost of a block
 // (elect, predicate set-up, the barrier polls) is paid per block, not per MMA.  Descriptors in 16-byte units: the A
 // operand of tap row r starts `arow` units after row r - 1, the filter slice `brow` units; the second K step is 2 units
@@ -475,6 +502,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // polls the barrier the next group needs (`full` of the next ring stage, or the `tempty` of the next tile's
     // accumulator when this is a tile's last k-block), so the blocking waits below normally fall through.
     const uint32_t idesc = instr_desc(kTileM, p.BN, 0, p.b_mn);
+    // descriptor = launch constant (swizzle mode, LBO / SBO) + the tile's shared-memory address in 16-byte units.
+    // B: K-major filter slice [BN][64], or (b_mn) BN / 64 MN-major atoms [64 k][64 c] straight from the untransposed
+    // filter: LBO = one 8 KB atom, 16 k-rows per MMA = 2048 B; k32: 64-byte rows in 64-byte-swizzled tiles (8-row groups
+    // 512 B apart), two MMAs per stage
+    const uint64_t a_const = p.k32 ? smem_desc64(0, 512) : smem_desc(0, 0, 1024);
+    const uint64_t b_const = p.k32 ? smem_desc64(0, 512) : (p.b_mn ? smem_desc(0, 8192, 1024) : smem_desc(0, 0, 1024));
+    const uint64_t b_kstep = p.b_mn ? 128ull : 2ull;
+    const uint32_t mode_flags = p.k32 ? kTwoMma : 0u;
+    const uint32_t ring_lo = smem_u32(smem) >> 4, stage_step = stage_bytes >> 4, a_off = a_bytes >> 4;
+    const uint32_t bres_lo = smem_u32(bres) >> 4, b_slice = b_bytes >> 4;
+    const uint32_t bar_full = smem_u32(&bars->full[0]), bar_empty = smem_u32(&bars->empty[0]);
+    const uint32_t bar_tfull = smem_u32(&bars->tfull[0]), bar_tempty = smem_u32(&bars->tempty[0]);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
@@ -506,26 +545,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         phase = nphase;
         continue;
       }
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      // (everything that depends only on the launch -- descriptor constants, strides, the k32 / b_mn / resident-filter
+      //  modes -- is computed once above the tile loop: the issue loop is ~100 uniform-datapath instructions per stage
+      //  and bounds the narrow layers, ncu source view of the 3x3 64-channel fprop)
+      uint32_t b_res = bres_lo;                        // resident filter: slice kb
+      int kb = 0;
+      if (mode_flags == 0u) {
+        // all but the last k-block: switches fixed at compile time (mma4_steady)
+        for (; kb < p.kblocks - 1; ++kb) {
+          if (!full_ready) mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+          const uint32_t a_lo = ring_lo + (uint32_t)stage * stage_step;
+          const uint32_t b_lo = p.b_resident ? b_res : a_lo + a_off;
+          b_res += b_slice;
+          mma4_steady(tmem_d, a_const + a_lo, b_const + b_lo, idesc, (uint32_t)kb, bar_full + 8u * (uint32_t)nstage, nphase,
+                      bar_empty + 8u * (uint32_t)stage, full_ready, b_kstep);
+          stage = nstage;
+          phase = nphase;
+        }
+      }
+      for (; kb < p.kblocks; ++kb) {
         if (!full_ready) mbar_wait(&bars->full[stage], phase);
         tc_fence_after();
         int nstage = stage + 1;
         uint32_t nphase = phase;
         if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
         const bool last = kb == p.kblocks - 1;
-        const uint32_t flags = ((!last || more_tiles) ? kPoll1 : 0u) | ((last && more_tiles) ? kPoll2 : 0u) | kCommit1 |
-                               (last ? kCommit2 : 0u);
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t sb = p.b_resident ? smem_u32(bres + (size_t)kb * b_bytes) : sa + a_bytes;
-        // B: K-major filter slice [BN][64], or (b_mn) BN / 64 MN-major atoms [64 k][64 c] straight from the
-        // untransposed filter: LBO = one 8 KB atom, 16 k-rows per MMA = 2048 B; k32: 64-byte rows in 64-byte-swizzled
-        // tiles (8-row groups 512 B apart), two MMAs per stage
-        const uint64_t bdesc = p.k32 ? smem_desc64(sb, 512) : (p.b_mn ? smem_desc(sb, 8192, 1024) : smem_desc(sb, 0, 1024));
-        const uint64_t adesc = p.k32 ? smem_desc64(sa, 512) : smem_desc(sa, 0, 1024);
-        mma4_fused(tmem_d, adesc, bdesc, 2ull, idesc, (uint32_t)kb, flags | (p.k32 ? kTwoMma : 0u),
-                   smem_u32(&bars->full[nstage]), nphase, smem_u32(&bars->tempty[nacc]), nacc_parity,
-                   smem_u32(&bars->empty[stage]), smem_u32(&bars->tfull[acc]), full_ready, acc_ready,
-                   p.b_mn ? 128ull : 2ull);
+        const uint32_t flags = mode_flags | ((!last || more_tiles) ? kPoll1 : 0u) | ((last && more_tiles) ? kPoll2 : 0u) |
+                               kCommit1 | (last ? kCommit2 : 0u);
+        const uint32_t a_lo = ring_lo + (uint32_t)stage * stage_step;
+        const uint32_t b_lo = p.b_resident ? b_res : a_lo + a_off;
+        b_res += b_slice;
+        mma4_fused(tmem_d, a_const + a_lo, b_const + b_lo, 2ull, idesc, (uint32_t)kb, flags,
+                   bar_full + 8u * (uint32_t)nstage, nphase, bar_tempty + 8u * (uint32_t)nacc, nacc_parity,
+                   bar_empty + 8u * (uint32_t)stage, bar_tfull + 8u * (uint32_t)acc, full_ready, acc_ready, b_kstep);
         stage = nstage;
         phase = nphase;
       }
@@ -1050,6 +1106,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     // stage's `full` barrier (and the next item's accumulator when this is the item's last brick), the last tap's
     // block commits.
     const uint32_t idesc = instr_desc(kTileM, p.BNc, 1, 1);
+    // dY: MN-major, 128B swizzle: LBO = bytes between 64-element atoms along M/N, SBO = 1024 (8 pixel rows); 16 pixels per
+    // MMA = 2 swizzle row groups = 2048 B = descriptor step 128.  X: the same, or (row stems) MN-major without swizzle --
+    // window chunks 16 B apart along N, 8-pixel groups 128 B apart along K, 16 pixels (256 B) per MMA
+    const uint64_t a_const = smem_desc(0, atom_bytes, 1024);
+    const uint64_t b_const = p.vw_rows ? (p.vw_rows == 1 ? smem_desc_plain(0, 128, 16) : smem_desc_plain(0, 16, 128))
+                                       : smem_desc(0, atom_bytes, 1024);
+    const uint64_t b_kstep = p.vw_rows ? 16ull : 128ull;
+    const uint32_t ring_lo = smem_u32(smem) >> 4, stage_step = stage_bytes >> 4, a_off = a_bytes >> 4;
+    const uint32_t b_slice = (p.vw_rows ? kVwgRowPitch : b_bytes) >> 4;
+    const uint32_t bar_full = smem_u32(&bars->full[0]), bar_empty = smem_u32(&bars->empty[0]);
+    const uint32_t bar_tfull = smem_u32(&bars->tfull[0]), bar_tempty = smem_u32(&bars->tempty[0]);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
@@ -1075,25 +1142,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         uint32_t nphase = phase;
         if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
         const bool last = b == b1 - 1;
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        // MN-major, 128B swizzle: LBO = bytes between 64-element atoms along M/N, SBO = 1024 (8 pixel rows);
-        // 16 pixels per MMA = 2 swizzle row groups = 2048 B = descriptor step 128
-        const uint64_t adesc = smem_desc(sa, atom_bytes, 1024);
+        // descriptor = launch constant + shared-memory address in 16-byte units (constants hoisted above the item loop)
+        const uint32_t a_lo = ring_lo + (uint32_t)stage * stage_step;
+        const uint64_t adesc = a_const + a_lo;
+        uint32_t b_lo = a_lo + a_off;
         uint32_t r1 = 0, r2 = 0;
         for (int j = 0; j < nt; ++j) {
           uint32_t flags = 0, q1, q2;
           if (j == 0) flags |= ((!last || more_items) ? kPoll1 : 0u) | ((last && more_items) ? kPoll2 : 0u);
           if (j == nt - 1) flags |= kCommit1 | (last ? kCommit2 : 0u);
-          // row stems: MN-major without swizzle -- window chunks 16 B apart along N, 8-pixel groups 128 B apart
-          // along K, 16 pixels (256 B) per MMA
-          const uint64_t bdesc = p.vw_rows
-              ? (p.vw_rows == 1 ? smem_desc_plain(sa + a_bytes + (uint32_t)j * kVwgRowPitch, 128, 16)
-                                : smem_desc_plain(sa + a_bytes + (uint32_t)j * kVwgRowPitch, 16, 128))
-              : smem_desc(sa + a_bytes + j * b_bytes, atom_bytes, 1024);
-          mma4_fused(tmem_d + (uint32_t)(j * p.BNc), adesc, bdesc, 128ull,
-                     idesc, (uint32_t)(b - b0), flags, smem_u32(&bars->full[nstage]), nphase,
-                     smem_u32(&bars->tempty[nacc]), nacc_parity, smem_u32(&bars->empty[stage]),
-                     smem_u32(&bars->tfull[acc]), q1, q2, p.vw_rows ? 16ull : 128ull);
+          mma4_fused(tmem_d + (uint32_t)(j * p.BNc), adesc, b_const + b_lo, 128ull,
+                     idesc, (uint32_t)(b - b0), flags, bar_full + 8u * (uint32_t)nstage, nphase,
+                     bar_tempty + 8u * (uint32_t)nacc, nacc_parity, bar_empty + 8u * (uint32_t)stage,
+                     bar_tfull + 8u * (uint32_t)acc, q1, q2, b_kstep);
+          b_lo += b_slice;
           if (j == 0) { r1 = q1; r2 = q2; }
         }
         full_ready = r1;
