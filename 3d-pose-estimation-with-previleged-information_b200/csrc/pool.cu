@@ -115,6 +115,63 @@ __global__ void __launch_bounds__(256) maxpool_bwd8_kernel(const bf16* __restric
   }
 }
 
+// The same gather with a 2 x 2 input block per thread: the four inputs (2a + di, 2b + dj) only ever look at the four output
+// windows (a + u, b + v), so one thread loads those four (gradient, argmax) vectors once and serves all four inputs --
+// 4 window loads per 4 inputs instead of 9 (1 / 2 / 2 / 4 by parity).
+__global__ void __launch_bounds__(256) maxpool_bwd8_block_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ argmax,
+                                                                bf16* __restrict__ dx, int N, int H, int W, int C, int Ho,
+                                                                int Wo) {
+  const int C8 = C >> 3, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+  const int per_row = W2 * C8;
+  for (int rp = blockIdx.x; rp < N * H2; rp += gridDim.x) {
+    const int n = rp / H2, a = rp - n * H2;
+    for (int j = threadIdx.x; j < per_row; j += blockDim.x) {
+      const int b = j / C8, cg = j - b * C8;
+      uint4 g[2][2];
+      uint2 am[2][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int oh = a + u, ow = b + v;
+          g[u][v] = make_uint4(0u, 0u, 0u, 0u);
+          am[u][v] = make_uint2(0xffffffffu, 0xffffffffu);              // matches no window position
+          if (oh < Ho && ow < Wo) {
+            const size_t op = (((size_t)n * Ho + oh) * Wo + ow) * C + cg * 8;
+            g[u][v] = *reinterpret_cast<const uint4*>(dy + op);
+            am[u][v] = *reinterpret_cast<const uint2*>(argmax + op);
+          }
+        }
+#pragma unroll
+      for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj) {
+          const int ih = 2 * a + di, iw = 2 * b + dj;
+          if (ih >= H || iw >= W) continue;
+          float acc[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+          for (int u = 0; u <= di; ++u)
+#pragma unroll
+            for (int v = 0; v <= dj; ++v) {
+              // position of (ih, iw) inside window (a + u, b + v): row di - 2u + 1, column dj - 2v + 1
+              const uint32_t code = (uint32_t)((di - 2 * u + 1) * 3 + (dj - 2 * v + 1)) * 0x01010101u;
+              const uint32_t m0 = __vcmpeq4(am[u][v].x, code), m1 = __vcmpeq4(am[u][v].y, code);
+              const uint32_t gw[4] = {g[u][v].x, g[u][v].y, g[u][v].z, g[u][v].w};
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const uint32_t mb = ((q < 4 ? m0 : m1) >> ((q & 3) * 8)) & 1u;
+                const float gv = __uint_as_float((q & 1) ? (gw[q >> 1] & 0xffff0000u) : (gw[q >> 1] << 16));
+                acc[q] += mb ? gv : 0.f;
+              }
+            }
+          store8(dx + (((size_t)n * H + ih) * W + iw) * C + cg * 8, acc);
+        }
+    }
+  }
+}
+
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, const float* __restrict__ veil_in, T* __restrict__ y,
                                    uint8_t* __restrict__ argmax, float* __restrict__ veil_out, int N, int H, int W,
@@ -239,7 +296,14 @@ extern "C" int b2_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, void* 
   if (dtype == B2_F32)
     maxpool_bwd_kernel<float><<<pool_grid(total), 256, 0, st>>>((const float*)dy, argmax, (float*)dx, N, H, W, C, Ho, Wo);
   else if ((C & 7) == 0)
-    maxpool_bwd8_kernel<<<row_grid((long long)N * H), 256, 0, st>>>((const bf16*)dy, argmax, (bf16*)dx, N, H, W, C, Ho, Wo);
+    {
+      static const bool per_pixel = getenv("B2POSE_POOL_BWD_PIXEL") && atoi(getenv("B2POSE_POOL_BWD_PIXEL")) != 0;   // A/B switch
+      if (per_pixel)
+        maxpool_bwd8_kernel<<<row_grid((long long)N * H), 256, 0, st>>>((const bf16*)dy, argmax, (bf16*)dx, N, H, W, C, Ho, Wo);
+      else
+        maxpool_bwd8_block_kernel<<<row_grid((long long)N * ((H + 1) / 2)), 256, 0, st>>>((const bf16*)dy, argmax, (bf16*)dx,
+                                                                                        N, H, W, C, Ho, Wo);
+    }
   else
     maxpool_bwd_kernel<bf16><<<pool_grid(total), 256, 0, st>>>((const bf16*)dy, argmax, (bf16*)dx, N, H, W, C, Ho, Wo);
   B2_LAUNCH_CHECK("maxpool_bwd");
