@@ -41,6 +41,27 @@ def test_header_arg_counts_match_binding(b2pose):
         assert n == len(args), (name, n, len(args))
 
 
+def test_flag_constants_match_header(b2pose):
+    """The binding's convolution flags are the header's enum values (a drifted flag would silently select another path)."""
+    src = open(os.path.join(ROOT, "include", "b2pose.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    header = {k: int(v) for k, v in re.findall(r"\bB2_(CONV_[A-Z_0-9]+)\s*=\s*(\d+)", src)}
+    assert len(header) >= 9 and header["CONV_X_CONCAT"] == 256
+    for name, value in header.items():
+        assert getattr(b2pose._lib, name) == value, name
+    assert int(re.search(r"#define\s+B2_ABI_VERSION\s+(\d+)", src).group(1)) == b2pose._lib.ABI_VERSION
+
+
+def test_tensor_pair_is_two_device_pointers(b2pose):
+    """B2_CONV_X_CONCAT operands travel as a host array of two pointers (here: CPU tensors, no launch)."""
+    a, b = torch.zeros(2, 3, 4, 8), torch.ones(2, 3, 4, 8)
+    pair = b2pose._lib.TensorPair(a, b)
+    arr = b2pose._lib.ptr(pair)
+    assert len(arr) == 2 and arr[0] == a.data_ptr() and arr[1] == b.data_ptr()
+    with pytest.raises(AssertionError):
+        b2pose._lib.TensorPair(a, torch.zeros(2, 3, 4, 16))
+
+
 def test_argument_validation_without_gpu(b2pose):
     """Bad descriptors are rejected on the host before any launch."""
     L = b2pose._lib
