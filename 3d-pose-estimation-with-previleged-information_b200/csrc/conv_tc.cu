@@ -248,6 +248,8 @@ __device__ __forceinline__ uint32_t produce_fused(uint32_t flags, uint32_t poll_
 }
 
 // wgrad producer stage: poll + expect_tx + the two dY atoms (k0, k0 + 64; 8 KB apart) + the first X atom.
+// flags bit 1 (value 2): the layer has at most 64 output channels -- the second atom is all zero, it is cleared once
+// at kernel start instead of being zero-filled by TMA for every stage.
 __device__ __forceinline__ uint32_t produce_wgrad_fused(uint32_t flags, uint32_t poll_bar, uint32_t poll_parity,
                                                         uint32_t full_bar, uint32_t tx_bytes, uint32_t dst_dy,
                                                         const CUtensorMap* map_dy, int k0, int ow0, int oh0, int n0,
@@ -255,16 +257,17 @@ __device__ __forceinline__ uint32_t produce_wgrad_fused(uint32_t flags, uint32_t
   uint32_t ready;
   asm volatile(
       "{\n\t"
-      ".reg .pred pw, pe, q;\n\t"
+      ".reg .pred pw, pe, q, p2;\n\t"
       ".reg .b32 t, d1, k1;\n\t"
       "and.b32 t, %1, 1;\n\tsetp.ne.b32 q, t, 0;\n\t"
       "setp.ne.b32 pw, 0, 0;\n\t"
       "@q mbarrier.test_wait.parity.shared::cta.b64 pw, [%2], %3;\n\t"
       "elect.sync _|pe, 0xffffffff;\n\t"
       "add.u32 d1, %6, 8192;\n\tadd.s32 k1, %8, 64;\n\t"
+      "and.b32 t, %1, 2;\n\tsetp.eq.b32 p2, t, 0;\n\tand.pred p2, p2, pe;\n\t"
       "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %5;\n\t"
       "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%6], [%7, {%8, %9, %10, %11}], [%4];\n\t"
-      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [d1], [%7, {k1, %9, %10, %11}], [%4];\n\t"
+      "@p2 cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [d1], [%7, {k1, %9, %10, %11}], [%4];\n\t"
       "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%12], [%13, {%14, %15, %16, %11}], [%4];\n\t"
       "selp.u32 %0, 1, 0, pw;\n\t"
       "}"
@@ -1032,11 +1035,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     if (p.split_c) prefetch_map(&map_x2);
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
+  // K <= 64: output channels 64..127 of the dY^T operand do not exist.  Their atom is cleared here once and never
+  // loaded (8 KB less operand feed per stage; the MMA still reads M = 128 rows)
+  const bool half_dy = p.K <= 64;
+  if (half_dy) {
+    for (int st = 0; st < p.stages; ++st)
+      for (uint32_t i = threadIdx.x * 16u; i < atom_bytes; i += kThreads * 16u)
+        sts128(smem_u32(smem + (size_t)st * stage_bytes + atom_bytes) + i, 0u, 0u, 0u, 0u);
+    fence_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);      // (warp-uniform for the compiler, see `warp`)
   pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
+  const uint32_t dy_flag = half_dy ? 2u : 0u, dy_tx = half_dy ? atom_bytes : a_bytes;
 
   // item decode: split fastest so CTAs running together share the same filter tile / spread pixels
   auto decode = [&](int item, int& sp, int& tg, int& ct, int& kt) {
@@ -1077,12 +1090,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const CUtensorMap* mx = second ? &map_x2 : &map_x;
         const int xc0 = ct * p.BNc - (second ? p.split_c : 0);
         if (p.vw_rows)     // one box: the seven raw rows (256-byte units of the padded row, 64 pixels = 4 units)
-          empty_ready = produce_wgrad_fused(has_next ? 1u : 0u, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
-                                            a_bytes + 7u * kVwgRowPitch, sa, &map_dy, kt * 128, ow0, oh0, n0,
+          empty_ready = produce_wgrad_fused((has_next ? 1u : 0u) | dy_flag, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
+                                            dy_tx + 7u * kVwgRowPitch, sa, &map_dy, kt * 128, ow0, oh0, n0,
                                             sa + a_bytes, &map_x, 0, ow0 >> 4, oh0 * 2);
         else
-        empty_ready = produce_wgrad_fused(has_next ? 1u : 0u, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
-                                          a_bytes + (uint32_t)nt * b_bytes, sa, &map_dy, kt * 128, ow0, oh0, n0,
+        empty_ready = produce_wgrad_fused((has_next ? 1u : 0u) | dy_flag, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
+                                          dy_tx + (uint32_t)nt * b_bytes, sa, &map_dy, kt * 128, ow0, oh0, n0,
                                           sa + a_bytes, mx, xc0, xw0 + s0 * p.dil, xh0 + r0 * p.dil);
         if (nt * atoms > 1) {
           if (elect_one()) {
@@ -1147,6 +1160,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const uint64_t adesc = a_const + a_lo;
         uint32_t b_lo = a_lo + a_off;
         uint32_t r1 = 0, r2 = 0;
+        if (!p.vw_rows) {
+          // The X tiles of the item's taps lie side by side (one atom stride apart, like the 64-channel atoms of a wide
+          // tile) and so do their accumulators: ONE MMA of N = nt * BNc columns per 16 pixels serves all taps of the
+          // group -- a third of the MMA instructions for the 64-channel 3x3 layers (N = 192), half for 128 channels
+          const uint32_t flags = ((!last || more_items) ? kPoll1 : 0u) | ((last && more_items) ? kPoll2 : 0u) | kCommit1 |
+                                 (last ? kCommit2 : 0u);
+          mma4_fused(tmem_d, adesc, b_const + b_lo, 128ull, instr_desc(kTileM, nt * p.BNc, 1, 1), (uint32_t)(b - b0), flags,
+                     bar_full + 8u * (uint32_t)nstage, nphase, bar_tempty + 8u * (uint32_t)nacc, nacc_parity,
+                     bar_empty + 8u * (uint32_t)stage, bar_tfull + 8u * (uint32_t)acc, r1, r2, b_kstep);
+        } else
         for (int j = 0; j < nt; ++j) {
           uint32_t flags = 0, q1, q2;
           if (j == 0) flags |= ((!last || more_items) ? kPoll1 : 0u) | ((last && more_items) ? kPoll2 : 0u);
