@@ -39,6 +39,9 @@ CASES = [
     ("stem_depth_256", 2, 1,   64,  256, 256, 7, 2, 3, 1, True,  True,  False),
     ("stem_rgb_wide", 1, 3,    64,  38, 300, 7, 2, 3, 1, False, False, False),
     ("stem_pc_257",   1, 1,    64,  41, 257, 7, 2, 3, 1, True,  False, False),
+    # 3x3 s1 p1, C = 64 at the widths of layer1 / layer5 (W % 64 == 0); K = 64 (second dY atom never loaded) and K = 128
+    ("wg_halo_64",    2, 64,   64,  20, 64, 3, 1, 1, 1, False, False, False),
+    ("wg_halo_128pc", 1, 64,   128, 9, 128, 3, 1, 1, 1, True,  True,  False),
     ("smallc_5x5",    2, 3,    32,  20, 20, 5, 1, 2, 1, False, False, False),
     # halo-tile mode (3x3 stride 1, Ho % 16 == 0, Wo % 8 == 0): several tiles per image, two channel blocks
     ("halo_48x40",    3, 128,  64,  48, 40, 3, 1, 1, 1, False, False, False),
