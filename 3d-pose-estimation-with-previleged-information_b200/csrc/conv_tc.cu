@@ -995,6 +995,7 @@ struct WgradParams {
   int bricks_per_split;
   int stages, tmem_cols;
   int split_c;                     // B2_CONV_X_CONCAT: input channels >= split_c come from the second tensor (map_x2)
+  int debug;                       // timing experiments (B2POSE_TC_DEBUG): 1 no reduction into dW, 8 no operand loads, 32 no MMAs
   int vw_rows;                     // row stems: a stage holds the brick's seven raw input rows [7][kVwgRowPitch]; the X
                                    // operand of tap row r is an MN-major no-swizzle descriptor over row r (pixel p,
                                    // window chunk c -> raw chunk p + c), 32 window elements per tap row; 1 / 2 selects
@@ -1084,6 +1085,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const uint32_t fb = smem_u32(&bars->full[stage]);
         const int xw0 = ow0 * p.stride_w - p.pad_w, xh0 = oh0 * p.stride - p.pad;
         const bool has_next = b + 1 < b1 || more_items;
+        if (p.debug & 8) {                           // timing experiment: no operand loads
+          empty_ready = 0;
+          if (lane == 0) mbar_arrive(&bars->full[stage]);
+          __syncwarp();
+          if (++wi == p.tiles_w) { wi = 0; if (++hi == p.tiles_h) { hi = 0; ++ni; } }
+          stage = nstage;
+          phase = nphase;
+          continue;
+        }
         // dy atoms: k channels [kt*128, +64) and [+64, +128); first x atom of the first tap
         // (channel concatenation of two inputs: a channel tile lies in one of them, split_c % BNc == 0)
         const bool second = p.split_c != 0 && ct * p.BNc >= p.split_c;
@@ -1160,7 +1170,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const uint64_t adesc = a_const + a_lo;
         uint32_t b_lo = a_lo + a_off;
         uint32_t r1 = 0, r2 = 0;
-        if (!p.vw_rows) {
+        if (p.debug & 32) {                          // timing experiment: no MMAs, only the barrier traffic
+          if (lane == 0) {
+            mbar_arrive(&bars->empty[stage]);
+            if (last) mbar_arrive(&bars->tfull[acc]);
+          }
+          __syncwarp();
+          r1 = r2 = 0;
+        } else if (!p.vw_rows) {
           // The X tiles of the item's taps lie side by side (one atom stride apart, like the 64-channel atoms of a wide
           // tile) and so do their accumulators: ONE MMA of N = nt * BNc columns per 16 pixels serves all taps of the
           // group -- a third of the MMA instructions for the 64-channel 3x3 layers (N = 192), half for 128 channels
@@ -1207,7 +1224,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           tmem_ld16(taddr + c0, v);
           tmem_ld16(taddr + c0 + 16, v + 16);
           tmem_ld_wait();
-          if (k < p.K) {
+          if (k < p.K && !(p.debug & 1)) {
 #pragma unroll
             for (int jj = 0; jj < 32; jj += 4)       // 16-byte vector reductions (C % 8 == 0 keeps groups whole)
               if (ct * p.BNc + c0 + jj < p.C)
@@ -2070,9 +2087,13 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   // stages, and the kernel runs on the side stream beside the BatchNorm / dgrad chain.  Measured in the step
   // (B2POSE_WGRAD_WAVES = 1 / 2 / 3 / 12): 14.74 / 14.85 / 15.1 / 14.65 ms -- one wave of work items for the 1x1 layers,
   // two for the multi-tap layers (whose few (tap group, tile) items need the splits for parallelism) = 12, the default
-  static const int env_waves = getenv("B2POSE_WGRAD_WAVES") ? atoi(getenv("B2POSE_WGRAD_WAVES")) : 12;
+  // End of round 2 (faster issue loops, fewer other atomics): 1 / 2-for-multi-tap / 3 waves = 13.35 / 13.48 / 13.92 ms --
+  // one wave for every layer (half the reduction traffic of the multi-tap layers: ncu-free timing with
+  // B2POSE_TC_DEBUG=1 shows the reduction at 30-36 % of the 128- and 256-channel 3x3 wgrads).  The split count is rounded
+  // DOWN so that the items fill whole waves (99 splits x 3 tap groups = 297 items had run as three rounds on 148 SMs).
+  static const int env_waves = getenv("B2POSE_WGRAD_WAVES") ? atoi(getenv("B2POSE_WGRAD_WAVES")) : 1;
   const int waves = env_waves == 12 ? (taps == 1 ? 1 : 2) : env_waves;
-  long long want = ((long long)waves * b2_num_sms() + base_items - 1) / base_items;
+  long long want = ((long long)waves * b2_num_sms()) / base_items;
   long long max_splits = (bricks + 7) / 8;
   if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
@@ -2090,6 +2111,8 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.T * p.BNc);
   p.dw = dw_out;
+  static const int env_debug_w = getenv("B2POSE_TC_DEBUG") ? atoi(getenv("B2POSE_TC_DEBUG")) : 0;
+  p.debug = env_debug_w;
   CUtensorMap mdy, mx, mx2;
   int rc = make_act_map(&mdy, dys, d->N, d->Ho, d->Wo, d->K, p.BW, p.BH, p.BNI, 1);
   if (rc) return rc;
