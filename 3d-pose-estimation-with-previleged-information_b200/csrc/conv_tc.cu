@@ -996,6 +996,11 @@ struct WgradParams {
   int stages, tmem_cols;
   int split_c;                     // B2_CONV_X_CONCAT: input channels >= split_c come from the second tensor (map_x2)
   int debug;                       // timing experiments (B2POSE_TC_DEBUG): 1 no reduction into dW, 8 no operand loads, 32 no MMAs
+  int halo;                        // 3x3 stride-1 pad-1 layers with 64 channels whose brick is 64 pixels of ONE image row:
+                                   // the three taps of a filter row read ONE 72-pixel X tile (pixels w0 - 1 .. w0 + 70).
+                                   // Tap s is the same tile shifted by s pixels = s x 128 B; the 128-byte swizzle follows the
+                                   // absolute shared-memory address, so the three taps are the three 64-column atoms of ONE
+                                   // N = 192 MN-major operand with LBO = 128 B (matrix base offset 0)
   int vw_rows;                     // row stems: a stage holds the brick's seven raw input rows [7][kVwgRowPitch]; the X
                                    // operand of tap row r is an MN-major no-swizzle descriptor over row r (pixel p,
                                    // window chunk c -> raw chunk p + c), 32 window elements per tap row; 1 / 2 selects
@@ -1005,6 +1010,7 @@ struct WgradParams {
 constexpr int kWgPix = 64;         // pixels per stage
 constexpr uint32_t kVwgRowUnits = 5, kVwgRowPitch = kVwgRowUnits * 256;   // raw stem row of a 64-pixel brick: 67 x 16 B
 constexpr uint32_t kVwgRowsBytes = 9 * 1024;                              // seven of them, rounded to the swizzle atom
+constexpr uint32_t kHaloPix = 72, kHaloBytes = kHaloPix * 128;            // halo X tile of a 64-pixel brick (9 swizzle atoms)
 
 // Work item = (pixel split, tap group, c-tile, k-tile).  All T taps of a group read the same dY tile
 // (one TMA fetch) and their own shifted X tile; their accumulators sit side by side in TMEM.
@@ -1017,7 +1023,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   // stage: A = dy [2 atoms of 64 k][64 pix][128 B]  (16 KB), B = T x ( x [BNc/64 atoms][64 pix][128 B] )
   const uint32_t atom_bytes = kWgPix * 128;
   const uint32_t a_bytes = 2 * atom_bytes, b_bytes = (uint32_t)(p.BNc / 64) * atom_bytes;
-  const uint32_t stage_bytes = a_bytes + (p.vw_rows ? kVwgRowsBytes : (uint32_t)p.T * b_bytes);
+  const uint32_t stage_bytes = a_bytes + (p.vw_rows ? kVwgRowsBytes : p.halo ? kHaloBytes : (uint32_t)p.T * b_bytes);
   PipeBars* bars = reinterpret_cast<PipeBars*>(smem + (size_t)p.stages * stage_bytes);
   // the warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role branches and everything
   // computed inside them (ring counters, shared-memory addresses, MMA descriptors) on the uniform datapath
@@ -1099,7 +1105,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const bool second = p.split_c != 0 && ct * p.BNc >= p.split_c;
         const CUtensorMap* mx = second ? &map_x2 : &map_x;
         const int xc0 = ct * p.BNc - (second ? p.split_c : 0);
-        if (p.vw_rows)     // one box: the seven raw rows (256-byte units of the padded row, 64 pixels = 4 units)
+        if (p.halo)        // one box: 72 pixels of input row oh0 - 1 + r0, starting one pixel left of the brick
+          empty_ready = produce_wgrad_fused((has_next ? 1u : 0u) | dy_flag, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
+                                            dy_tx + kHaloBytes, sa, &map_dy, kt * 128, ow0, oh0, n0,
+                                            sa + a_bytes, mx, xc0, xw0, xh0 + r0 * p.dil);
+        else if (p.vw_rows)     // one box: the seven raw rows (256-byte units of the padded row, 64 pixels = 4 units)
           empty_ready = produce_wgrad_fused((has_next ? 1u : 0u) | dy_flag, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
                                             dy_tx + 7u * kVwgRowPitch, sa, &map_dy, kt * 128, ow0, oh0, n0,
                                             sa + a_bytes, &map_x, 0, ow0 >> 4, oh0 * 2);
@@ -1107,7 +1117,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         empty_ready = produce_wgrad_fused((has_next ? 1u : 0u) | dy_flag, smem_u32(&bars->empty[nstage]), nphase ^ 1, fb,
                                           dy_tx + (uint32_t)nt * b_bytes, sa, &map_dy, kt * 128, ow0, oh0, n0,
                                           sa + a_bytes, mx, xc0, xw0 + s0 * p.dil, xh0 + r0 * p.dil);
-        if (nt * atoms > 1) {
+        if (nt * atoms > 1 && !p.halo) {
           if (elect_one()) {
             int r = r0, s = s0;
             for (int j = 0; j < nt; ++j) {
@@ -1134,6 +1144,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     // window chunks 16 B apart along N, 8-pixel groups 128 B apart along K, 16 pixels (256 B) per MMA
     const uint64_t a_const = smem_desc(0, atom_bytes, 1024);
     const uint64_t b_const = p.vw_rows ? (p.vw_rows == 1 ? smem_desc_plain(0, 128, 16) : smem_desc_plain(0, 16, 128))
+                             : p.halo  ? smem_desc(0, 128, 1024)        // the three taps = three atoms one pixel row apart
                                        : smem_desc(0, atom_bytes, 1024);
     const uint64_t b_kstep = p.vw_rows ? 16ull : 128ull;
     const uint32_t ring_lo = smem_u32(smem) >> 4, stage_step = stage_bytes >> 4, a_off = a_bytes >> 4;
@@ -2069,12 +2080,18 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   }
   p.vw_rows = vw_rows;
   if (vw_rows) { p.BW = kWgPix; p.BH = 1; p.BNI = 1; }          // 64 pixels of one output row
+  // halo mode (WgradParams::halo): tap group = filter row, bricks of 64 pixels of one image row; B2POSE_WGRAD_HALO=0 disables
+  static const int env_halo = getenv("B2POSE_WGRAD_HALO") ? atoi(getenv("B2POSE_WGRAD_HALO")) : 1;
+  p.halo = (env_halo && !vw && !(d0->flags & B2_CONV_X_CONCAT) && d->R == 3 && d->S == 3 && d->stride == 1 &&
+            d->dil == 1 && d->pad == 1 && d->C == 64 && d->Wo % kWgPix == 0) ? 1 : 0;
+  if (p.halo) { p.BW = kWgPix; p.BH = 1; p.BNI = 1; }
   p.tiles_w = (d->Wo + p.BW - 1) / p.BW; p.tiles_h = (d->Ho + p.BH - 1) / p.BH; p.tiles_n = (d->N + p.BNI - 1) / p.BNI;
   p.BNc = vw_rows ? 32 : wgrad_bnc(d->C);
   p.ctiles = (d->C + p.BNc - 1) / p.BNc;
   p.ktiles = (d->K + 127) / 128;
   const int taps = d->R * d->S;
   p.T = 256 / p.BNc;                       // 2 accumulator sets x T x BNc <= 512 TMEM columns
+  if (p.halo) p.T = 3;                     // (one filter row per work item)
   if (vw_rows) p.T = 7;                    // (row stems: all seven tap rows share the dY tile, 2 x 7 x 32 columns)
   if (p.T > taps) p.T = taps;
   if (p.T < 1) p.T = 1;
@@ -2099,7 +2116,8 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   if (want < 1) want = 1;
   p.bricks_per_split = (int)((bricks + want - 1) / want);
   p.splits = (int)((bricks + p.bricks_per_split - 1) / p.bricks_per_split);
-  const int stage_bytes = 2 * kWgPix * 128 + (vw_rows ? (int)kVwgRowsBytes : p.T * (p.BNc / 64) * kWgPix * 128);
+  const int stage_bytes = 2 * kWgPix * 128 + (vw_rows ? (int)kVwgRowsBytes : p.halo ? (int)kHaloBytes
+                                                                             : p.T * (p.BNc / 64) * kWgPix * 128);
   // B2POSE_WGRAD_SMEM_KB caps the ring so that blocks of other kernels (the BatchNorm streams running on the
   // main stream while wgrad runs on the side stream) can share the SM
   static const int env_kb = getenv("B2POSE_WGRAD_SMEM_KB") ? atoi(getenv("B2POSE_WGRAD_SMEM_KB")) : 0;
@@ -2129,6 +2147,7 @@ int conv_tc_wgrad(const B2ConvDesc* d, const void* x, const float* mask_in, cons
   } else {
     rc = vw_rows ? make_vw_rows_map(&mx, x, d->N, vw_hp(d0), vw_wp(d0), kVwgRowUnits)
          : vw    ? make_vw_map(&mx, x, d->N, vw_hp(d0), vw_wp(d0), d->Wo, p.BW, p.BH, p.BNI)
+         : p.halo ? make_act_map(&mx, x, d->N, d->H, d->W, d->C, (int)kHaloPix, 1, 1, 1)
                  : make_act_map(&mx, x, d->N, d->H, d->W, d->C, p.BW, p.BH, p.BNI, d->stride);
     if (rc) return rc;
     mx2 = mx;
